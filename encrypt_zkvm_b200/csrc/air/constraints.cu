@@ -1,0 +1,155 @@
+// Fused constraint evaluation kernel (K5) and the divisor-inverse kernel.  See constraints.cuh.
+#include "constraints.cuh"
+#include "processor_air.cuh"
+#include "../common.h"
+
+namespace ezk {
+
+using namespace dev;
+
+namespace {
+
+constexpr int kBatch = 16;  // elements per thread in Montgomery batch inversion
+
+__device__ __forceinline__ fe ld2(const uint64_t v[2]) { return fe_make(v[0], v[1]); }
+
+// x_i = 3 * w_L^i
+__device__ __forceinline__ fe domain_point(const uint4* __restrict__ roots, uint32_t log_L, uint64_t i) {
+    fe w = fe_root_pow(roots, log_L, i);
+    return fe_add(fe_add(w, w), w);
+}
+
+__global__ void __launch_bounds__(128) pair_inverse_kernel(const uint4* __restrict__ roots, uint32_t log_L, fe a, fe b,
+                                                           uint4* __restrict__ out) {
+    const uint64_t L = 1ull << log_L;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    fe pre[kBatch];
+    fe acc = fe_one();
+#pragma unroll
+    for (int q = 0; q < kBatch; q++) {
+        uint64_t i = t + q * nthreads;
+        fe d = fe_one();
+        if (i < L) {
+            fe x = domain_point(roots, log_L, i);
+            d = fe_mul(fe_sub(x, a), fe_sub(x, b));
+        }
+        pre[q] = acc;
+        acc = fe_mul(acc, d);
+    }
+    acc = fe_inv(acc);
+#pragma unroll
+    for (int q = kBatch - 1; q >= 0; q--) {
+        uint64_t i = t + q * nthreads;
+        if (i < L) {
+            // recompute d_i instead of keeping a second register array
+            fe x = domain_point(roots, log_L, i);
+            fe d = fe_mul(fe_sub(x, a), fe_sub(x, b));
+            fe_store(out + i, fe_mul(acc, pre[q]));
+            acc = fe_mul(acc, d);
+        }
+    }
+}
+
+struct LdeFrame {
+    const uint4* __restrict__ lde;
+    uint64_t pitch, i, inext;
+    __device__ __forceinline__ fe cur(int c) const { return fe_ldg(lde + (uint64_t)c * pitch + i); }
+    __device__ __forceinline__ fe nxt(int c) const { return fe_ldg(lde + (uint64_t)c * pitch + inext); }
+};
+
+struct SumSink {
+    const ConstraintParams* __restrict__ p;
+    fe acc;
+    __device__ __forceinline__ void put(int j, fe v) { acc = fe_add(acc, fe_mul(ld2(p->tcoef[j]), v)); }
+};
+
+__global__ void __launch_bounds__(128) constraint_kernel(const uint4* __restrict__ roots, const uint4* __restrict__ lde,
+                                                         uint64_t pitch, uint32_t log_L,
+                                                         const ConstraintParams* __restrict__ p,
+                                                         const uint4* __restrict__ inv_den, uint4* __restrict__ combined) {
+    const uint64_t L = 1ull << log_L;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    LdeFrame f{lde, pitch, i, (i + 8) & (L - 1)};
+    fe periodic[9];
+    {
+        const uint64_t(*row)[2] = &p->ptable[(i & 127) * 9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) periodic[k] = ld2(row[k]);
+    }
+    SumSink sink{p, fe_zero()};
+    eval_transition(f, periodic, reinterpret_cast<const AirConsts*>(p->inv_mds), p->delta, sink);
+    const fe x = domain_point(roots, log_L, i);
+    const fe a = ld2(p->g_last);
+    // transition part: T * (x - g^(n-2)) (x - g^(n-1)) / (x^n - 1)
+    fe t = fe_mul(sink.acc, fe_mul(fe_sub(x, a), fe_sub(x, ld2(p->g_last2))));
+    t = fe_mul(t, ld2(p->inv_zn[i & 7]));
+    // boundary groups: step 0 (12 assertions, all values zero) and step n-2 (10 assertions)
+    fe s0 = fe_zero(), s1 = fe_zero();
+#pragma unroll
+    for (int k = 0; k < 12; k++) s0 = fe_add(s0, fe_mul(ld2(p->bcoef[k]), f.cur(p->bcol[k])));
+#pragma unroll
+    for (int k = 12; k < 22; k++) s1 = fe_add(s1, fe_mul(ld2(p->bcoef[k]), fe_sub(f.cur(p->bcol[k]), ld2(p->bval[k]))));
+    // B0/(x-1) + B1/(x-a) = (B0 (x-a) + B1 (x-1)) / ((x-1)(x-a))
+    fe num = fe_add(fe_mul(s0, fe_sub(x, a)), fe_mul(s1, fe_sub(x, fe_one())));
+    fe bsum = fe_mul(num, fe_ldg(inv_den + i));
+    fe_store(combined + i, fe_add(t, bsum));
+}
+
+struct ArrayFrame {
+    const uint4* c;
+    const uint4* n;
+    __device__ __forceinline__ fe cur(int k) const { return fe_load(c + k); }
+    __device__ __forceinline__ fe nxt(int k) const { return fe_load(n + k); }
+};
+struct StoreSink {
+    uint4* out;
+    __device__ __forceinline__ void put(int j, fe v) { fe_store(out + j, v); }
+};
+
+__global__ void frames_kernel(const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,
+                              const ConstraintParams* __restrict__ p, uint4* out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nframes) return;
+    ArrayFrame f{cur + 28 * t, nxt + 28 * t};
+    fe per[9];
+    for (int k = 0; k < 9; k++) per[k] = fe_load(periodic + 9 * t + k);
+    StoreSink sink{out + 20 * t};
+    eval_transition(f, per, reinterpret_cast<const AirConsts*>(p->inv_mds), p->delta, sink);
+}
+
+}  // namespace
+
+int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, uint32_t log_L, const uint64_t a[2], const uint64_t b[2],
+                        uint4* out) {
+    const uint64_t L = 1ull << log_L;
+    const unsigned threads = 128;
+    uint64_t need = (L + kBatch - 1) / kBatch;
+    unsigned blocks = (unsigned)((need + threads - 1) / threads);
+    pair_inverse_kernel<<<blocks, threads, 0, s>>>(root_fwd, log_L, fe_make(a[0], a[1]), fe_make(b[0], b[1]), out);
+    EZK_CUDA(cudaGetLastError());
+    count_launch();
+    return 1;
+}
+
+int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde, uint64_t pitch, uint32_t log_L,
+                         const ConstraintParams* params, const uint4* inv_den, uint4* combined) {
+    const uint64_t L = 1ull << log_L;
+    const unsigned threads = 128;
+    constraint_kernel<<<(unsigned)((L + threads - 1) / threads), threads, 0, s>>>(root_fwd, lde, pitch, log_L, params,
+                                                                                inv_den, combined);
+    EZK_CUDA(cudaGetLastError());
+    count_launch();
+    return 1;
+}
+
+int evaluate_frames(cudaStream_t s, const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,
+                    const ConstraintParams* params, uint4* out) {
+    frames_kernel<<<(nframes + 63) / 64, 64, 0, s>>>(cur, nxt, periodic, nframes, params, out);
+    EZK_CUDA(cudaGetLastError());
+    count_launch();
+    return 1;
+}
+
+}  // namespace ezk

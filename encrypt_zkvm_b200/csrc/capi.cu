@@ -1,0 +1,316 @@
+// extern "C" boundary (include/ezkvm_prover.h).  Plain pointers and sizes only; every C++ exception is
+// translated into an ezk_status code + thread-local message.
+#include "../../include/ezkvm_prover.h"
+#include "common.h"
+#include "host/vm.h"
+#include "prover.h"
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+using namespace ezk;
+
+struct ezk_prover {
+    std::unique_ptr<GpuProver> impl;
+    std::mutex mu;
+};
+struct ezk_program {
+    Program prog;
+};
+struct ezk_execution {
+    ExecutionTrace trace;
+};
+
+namespace {
+thread_local std::string g_error;
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return EZK_OK;
+    } catch (const ProveFailure& e) {
+        g_error = e.message;
+        return e.code;
+    } catch (const VmError& e) {
+        g_error = e.message;
+        return EZK_ERR_VM;
+    } catch (const CudaError& e) {
+        g_error = e.what();
+        return EZK_ERR_CUDA;
+    } catch (const std::bad_alloc&) {
+        g_error = "out of host memory";
+        return EZK_ERR_INTERNAL;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return EZK_ERR_INTERNAL;
+    }
+}
+
+ProofOptions to_options(const ezk_options* o) {
+    ProofOptions p;
+    if (o) {
+        p.num_queries = o->num_queries, p.blowup = o->blowup_factor, p.grinding = o->grinding_factor;
+        p.field_ext = o->field_extension, p.fri_fold = o->fri_folding_factor, p.fri_rem_max_deg = o->fri_remainder_max_degree;
+    }
+    return p;
+}
+
+PublicInputs to_public(const ezk_public_inputs* pi) {
+    if (!pi) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "public inputs are required"};
+    PublicInputs p;
+    for (int i = 0; i < 2; i++) p.elements[i] = fp_load(pi->program_hash[i]);
+    for (int i = 0; i < 16; i++) p.elements[2 + i] = fp_load(pi->stack_outputs[i]);
+    for (int i = 0; i < 18; i++)
+        if (p.elements[i].v >= Fp::modulus()) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "public input is not a canonical field element"};
+    p.lwe_k = pi->lwe_k, p.lwe_delta = pi->lwe_delta;
+    return p;
+}
+
+void export_proof(std::vector<uint8_t>& bytes, uint8_t** proof, size_t* proof_len) {
+    uint8_t* out = static_cast<uint8_t*>(malloc(bytes.size()));
+    if (!out) throw std::bad_alloc();
+    memcpy(out, bytes.data(), bytes.size());
+    *proof = out;
+    *proof_len = bytes.size();
+}
+
+ezk_prover* g_default = nullptr;
+std::mutex g_default_mu;
+}  // namespace
+
+extern "C" {
+
+const char* ezk_last_error(void) { return g_error.c_str(); }
+const char* ezk_version(void) { return "encrypt-zkvm-b200 0.1 (sm_100a)"; }
+int ezk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+uint64_t ezk_kernel_launch_count(void) { return launch_count(); }
+void ezk_free(void* p) { free(p); }
+void ezk_default_options(ezk_options* out) {
+    if (!out) return;
+    out->num_queries = 32, out->blowup_factor = 8, out->grinding_factor = 0, out->field_extension = 1;
+    out->fri_folding_factor = 8, out->fri_remainder_max_degree = 127;
+}
+
+int ezk_prover_create(int device, ezk_prover** out) {
+    return guarded([&] {
+        if (!out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "out pointer is null"};
+        auto p = std::make_unique<ezk_prover>();
+        p->impl = std::make_unique<GpuProver>(device);
+        *out = p.release();
+    });
+}
+void ezk_prover_destroy(ezk_prover* p) { delete p; }
+
+int ezk_prover_prove(ezk_prover* p, const ezk_trace* trace, const ezk_public_inputs* pub, const ezk_options* opt,
+                     uint8_t** proof, size_t* proof_len) {
+    return guarded([&] {
+        if (!p || !trace || !proof || !proof_len || !trace->columns) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        if (trace->width != EZK_TRACE_WIDTH) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "trace width must be 28"};
+        for (uint32_t c = 0; c < trace->width; c++)
+            if (!trace->columns[c]) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null trace column"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        auto bytes = p->impl->prove(trace->columns, nullptr, trace->length, to_public(pub), to_options(opt));
+        export_proof(bytes, proof, proof_len);
+    });
+}
+
+int ezk_prover_prove_device(ezk_prover* p, const void* d_trace, uint64_t length, const ezk_public_inputs* pub,
+                            const ezk_options* opt, uint8_t** proof, size_t* proof_len) {
+    return guarded([&] {
+        if (!p || !d_trace || !proof || !proof_len) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        auto bytes = p->impl->prove(nullptr, static_cast<const uint4*>(d_trace), length, to_public(pub), to_options(opt));
+        export_proof(bytes, proof, proof_len);
+    });
+}
+
+int ezk_prove(const ezk_trace* trace, const ezk_public_inputs* pub, const ezk_options* opt, uint8_t** proof,
+              size_t* proof_len) {
+    {
+        std::lock_guard<std::mutex> lock(g_default_mu);
+        if (!g_default) {
+            int rc = ezk_prover_create(0, &g_default);
+            if (rc != EZK_OK) return rc;
+        }
+    }
+    return ezk_prover_prove(g_default, trace, pub, opt, proof, proof_len);
+}
+
+int ezk_prover_stage_times(const ezk_prover* p, float* ms_out) {
+    return guarded([&] {
+        if (!p || !ms_out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        memcpy(ms_out, p->impl->stage_ms(), EZK_STAGE_COUNT * sizeof(float));
+    });
+}
+
+int ezk_prover_artifact(ezk_prover* p, int which, void* dst, size_t cap, size_t* size_out) {
+    return guarded([&] {
+        if (!p) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        auto bytes = p->impl->artifact(which);
+        if (size_out) *size_out = bytes.size();
+        if (dst) memcpy(dst, bytes.data(), std::min(cap, bytes.size()));
+    });
+}
+
+int ezk_stage_lde(ezk_prover* p, const void* columns, uint32_t width, uint64_t n, void* lde_out) {
+    return guarded([&] {
+        if (!p || !columns || !lde_out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->stage_lde(columns, width, n, lde_out);
+    });
+}
+int ezk_stage_ntt(ezk_prover* p, const void* columns, uint32_t width, uint64_t n, int inverse, void* out) {
+    return guarded([&] {
+        if (!p || !columns || !out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->stage_ntt(columns, width, n, inverse != 0, out);
+    });
+}
+int ezk_stage_merkle(ezk_prover* p, const void* table, uint32_t width, uint64_t rows, void* nodes_out) {
+    return guarded([&] {
+        if (!p || !table || !nodes_out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->stage_merkle(table, width, rows, nodes_out);
+    });
+}
+int ezk_stage_fri_fold(ezk_prover* p, const void* evals, uint64_t s, const void* alpha16, void* next_out) {
+    return guarded([&] {
+        if (!p || !evals || !alpha16 || !next_out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->stage_fri_fold(evals, s, fp_load(static_cast<const uint8_t*>(alpha16)), next_out);
+    });
+}
+int ezk_stage_eval_frames(ezk_prover* p, const void* cur, const void* next, const void* periodic, uint32_t nframes,
+                          uint32_t lwe_delta, void* out20) {
+    return guarded([&] {
+        if (!p || !cur || !next || !periodic || !out20 || !nframes) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->stage_eval_frames(cur, next, periodic, nframes, lwe_delta, out20);
+    });
+}
+int ezk_bench_lde_merkle(ezk_prover* p, uint32_t width, uint64_t n, int iters, float* lde_ms, float* merkle_ms) {
+    return guarded([&] {
+        if (!p || !lde_ms || !merkle_ms) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->bench_lde_merkle(width, n, iters, lde_ms, merkle_ms);
+    });
+}
+int ezk_bench_fri(ezk_prover* p, uint64_t n, int iters, float* fri_ms) {
+    return guarded([&] {
+        if (!p || !fri_ms) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->bench_fri(n, iters, fri_ms);
+    });
+}
+
+// ---- host VM ----
+int ezk_program_compile(const char* source, ezk_program** out) {
+    return guarded([&] {
+        if (!source || !out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        auto p = std::make_unique<ezk_program>();
+        p->prog = Program::compile(source);
+        *out = p.release();
+    });
+}
+void ezk_program_free(ezk_program* p) { delete p; }
+size_t ezk_program_len(const ezk_program* p) { return p ? p->prog.code.size() : 0; }
+void ezk_program_ops(const ezk_program* p, uint8_t* codes, uint8_t* values) {
+    if (!p) return;
+    for (size_t i = 0; i < p->prog.code.size(); i++) {
+        if (codes) codes[i] = p->prog.code[i].code;
+        if (values) values[i] = p->prog.code[i].value;
+    }
+}
+void ezk_program_hash(const ezk_program* p, uint8_t out[2][16]) {
+    if (!p) return;
+    fp_store(out[0], p->prog.hash[0]);
+    fp_store(out[1], p->prog.hash[1]);
+}
+size_t ezk_program_display(const ezk_program* p, char* dst, size_t cap) {
+    if (!p) return 0;
+    std::string s = p->prog.to_string();
+    if (dst && cap) {
+        size_t k = std::min(cap - 1, s.size());
+        memcpy(dst, s.data(), k);
+        dst[k] = 0;
+    }
+    return s.size() + 1;
+}
+
+int ezk_vm_execute(const ezk_program* prog, const uint8_t* public_tape, size_t public_len, const void* secret_elems,
+                   size_t num_ciphertexts, uint32_t lwe_k, uint32_t lwe_delta, uint64_t last_row_seed,
+                   ezk_execution** out) {
+    return guarded([&] {
+        if (!prog || !out || (public_len && !public_tape) || (num_ciphertexts && !secret_elems))
+            throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        LweParams lwe;
+        lwe.k = lwe_k, lwe.delta = lwe_delta;
+        std::vector<uint8_t> pub(public_tape, public_tape + public_len);
+        std::vector<Fp> secret(num_ciphertexts * lwe.lwe_size());
+        for (size_t i = 0; i < secret.size(); i++) secret[i] = fp_load(static_cast<const uint8_t*>(secret_elems) + 16 * i);
+        auto e = std::make_unique<ezk_execution>();
+        e->trace = execute(prog->prog, pub, secret, lwe, last_row_seed);
+        *out = e.release();
+    });
+}
+void ezk_execution_free(ezk_execution* e) { delete e; }
+uint64_t ezk_execution_length(const ezk_execution* e) { return e ? e->trace.n : 0; }
+const uint8_t* ezk_execution_column(const ezk_execution* e, uint32_t c) {
+    if (!e || c >= e->trace.columns.size()) return nullptr;
+    return reinterpret_cast<const uint8_t*>(e->trace.columns[c].data());
+}
+void ezk_execution_outputs(const ezk_execution* e, uint8_t out[16][16]) {
+    if (!e) return;
+    for (int i = 0; i < 16; i++) fp_store(out[i], e->trace.outputs[i]);
+}
+
+int ezk_synthetic_case(int kind, uint32_t log_n, uint32_t lwe_k, uint32_t lwe_delta, uint64_t seed, ezk_program** prog,
+                       ezk_execution** exec) {
+    return guarded([&] {
+        if (!prog || !exec || kind < 1 || kind > 3 || log_n < 7 || log_n > 26)
+            throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad synthetic case parameters"};
+        LweParams lwe;
+        lwe.k = lwe_k, lwe.delta = lwe_delta;
+        SyntheticCase c = make_synthetic(kind, log_n, lwe, seed);
+        auto e = std::make_unique<ezk_execution>();
+        e->trace = execute(c.program, c.pub, c.secret, lwe, seed ^ 0x5EEDULL);
+        auto p = std::make_unique<ezk_program>();
+        p->prog = std::move(c.program);
+        *prog = p.release();
+        *exec = e.release();
+    });
+}
+
+void ezk_lwe_keygen(uint32_t k, uint64_t seed, void* key_out) {
+    LweParams p;
+    p.k = k;
+    LweKey key = lwe_keygen(p, seed);
+    for (uint32_t i = 0; i < k; i++) fp_store(static_cast<uint8_t*>(key_out) + 16 * i, key.key[i]);
+}
+void ezk_lwe_encrypt(const void* key, uint32_t k, uint32_t delta, double std_dev, uint8_t value, uint64_t seed,
+                     void* ct_out) {
+    LweKey lk;
+    lk.params.k = k, lk.params.delta = delta, lk.params.std_dev = std_dev;
+    for (uint32_t i = 0; i < k; i++) lk.key.push_back(fp_load(static_cast<const uint8_t*>(key) + 16 * i));
+    auto ct = lwe_encrypt(lk, value, seed);
+    for (uint32_t i = 0; i <= k; i++) fp_store(static_cast<uint8_t*>(ct_out) + 16 * i, ct[i]);
+}
+uint8_t ezk_lwe_decrypt(const void* key, uint32_t k, uint32_t delta, const void* ct) {
+    LweKey lk;
+    lk.params.k = k, lk.params.delta = delta;
+    for (uint32_t i = 0; i < k; i++) lk.key.push_back(fp_load(static_cast<const uint8_t*>(key) + 16 * i));
+    std::vector<Fp> c(k + 1);
+    for (uint32_t i = 0; i <= k; i++) c[i] = fp_load(static_cast<const uint8_t*>(ct) + 16 * i);
+    return lwe_decrypt(lk, c.data());
+}
+
+}  // extern "C"

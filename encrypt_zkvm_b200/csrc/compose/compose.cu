@@ -1,0 +1,141 @@
+// OOD evaluation + DEEP composition kernels (K7, K8).  See compose.cuh.
+#include "compose.cuh"
+#include "../common.h"
+#include "../field/f128.cuh"
+
+namespace ezk {
+
+using namespace dev;
+
+namespace {
+
+constexpr int kEvalThreads = 256;
+constexpr uint32_t kEvalChunkLog = 14;  // coefficients per block
+
+// block (bx, col): partial sums over coefficients [bx*chunk, (bx+1)*chunk) at up to 2 points.
+// thread t owns m = base + t + q*T: acc = sum_q a[m] Y^q (Horner, Y = y^T), then times y^(base + t).
+__global__ void __launch_bounds__(kEvalThreads) eval_partial_kernel(const uint4* __restrict__ coeff, uint64_t pitch,
+                                                                   uint32_t log_n, fe y0, fe y1, uint32_t npoints,
+                                                                   uint4* __restrict__ scratch) {
+    __shared__ uint4 red[2][kEvalThreads];
+    const uint64_t n = 1ull << log_n;
+    const uint64_t chunk = n < (1ull << kEvalChunkLog) ? n : (1ull << kEvalChunkLog);
+    const uint64_t base = (uint64_t)blockIdx.x * chunk;
+    const uint4* col = coeff + (uint64_t)blockIdx.y * pitch;
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    fe ys[2] = {y0, y1};
+    fe acc[2] = {fe_zero(), fe_zero()};
+    if (t < chunk) {
+        fe Y[2];
+        for (uint32_t k = 0; k < npoints; k++) Y[k] = fe_pow(ys[k], T);
+        const uint64_t iters = (chunk - t + T - 1) / T;
+        for (uint64_t q = iters; q-- > 0;) {
+            fe a = fe_ldg(col + base + t + q * T);
+            for (uint32_t k = 0; k < npoints; k++) acc[k] = fe_add(fe_mul(acc[k], Y[k]), a);
+        }
+        for (uint32_t k = 0; k < npoints; k++) acc[k] = fe_mul(acc[k], fe_pow(ys[k], base + t));
+    }
+    for (uint32_t k = 0; k < npoints; k++) fe_store(&red[k][t], acc[k]);
+    __syncthreads();
+    for (uint32_t h = T / 2; h >= 1; h >>= 1) {
+        if (t < h)
+            for (uint32_t k = 0; k < npoints; k++)
+                fe_store(&red[k][t], fe_add(fe_load(&red[k][t]), fe_load(&red[k][t + h])));
+        __syncthreads();
+    }
+    if (t < npoints) scratch[((uint64_t)blockIdx.y * npoints + t) * gridDim.x + blockIdx.x] = red[t][0];
+}
+
+__global__ void eval_final_kernel(const uint4* __restrict__ scratch, uint32_t nblocks, uint32_t nout,
+                                  uint4* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nout) return;
+    fe acc = fe_zero();
+    for (uint32_t b = 0; b < nblocks; b++) acc = fe_add(acc, fe_load(scratch + (uint64_t)t * nblocks + b));
+    fe_store(out + t, acc);
+}
+
+__global__ void __launch_bounds__(256) deep_combine_kernel(const uint4* __restrict__ tcoeff, uint64_t tpitch,
+                                                          const uint4* __restrict__ ccoeff, uint64_t cpitch, uint64_t n,
+                                                          const uint4* __restrict__ dc, uint4* __restrict__ pq) {
+    uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    fe p = fe_zero(), q = fe_zero();
+#pragma unroll 4
+    for (int c = 0; c < 28; c++) p = fe_add(p, fe_mul(fe_ldg(dc + c), fe_ldg(tcoeff + (uint64_t)c * tpitch + m)));
+#pragma unroll
+    for (int j = 0; j < 7; j++) q = fe_add(q, fe_mul(fe_ldg(dc + 28 + j), fe_ldg(ccoeff + (uint64_t)j * cpitch + m)));
+    fe_store(pq + m, p);
+    fe_store(pq + n + m, q);
+}
+
+__global__ void __launch_bounds__(256) deep_pointwise_kernel(const uint4* __restrict__ roots,
+                                                            const uint4* __restrict__ pq_lde, uint32_t log_L,
+                                                            const uint4* __restrict__ inv_den, DeepScalars sc,
+                                                            uint4* __restrict__ deep) {
+    const uint64_t L = 1ull << log_L;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    fe w = fe_root_pow(roots, log_L, i);
+    fe x = fe_add(fe_add(w, w), w);
+    fe P = fe_ldg(pq_lde + i), Q = fe_ldg(pq_lde + L + i);
+    fe t1 = fe_sub(fe_add(P, Q), fe_make(sc.s1[0], sc.s1[1]));
+    fe t2 = fe_sub(P, fe_make(sc.s2[0], sc.s2[1]));
+    fe num = fe_add(fe_mul(t1, fe_sub(x, fe_make(sc.zg[0], sc.zg[1]))), fe_mul(t2, fe_sub(x, fe_make(sc.z[0], sc.z[1]))));
+    fe_store(deep + i, fe_mul(num, fe_ldg(inv_den + i)));
+}
+
+__global__ void all_zero_kernel(const uint4* __restrict__ v, uint64_t count, uint32_t* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bad = 0;
+    for (; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 x = __ldg(v + i);
+        bad |= (x.x | x.y | x.z | x.w) != 0;
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+}  // namespace
+
+int eval_polys(cudaStream_t s, const uint4* coeff, uint64_t pitch, uint32_t ncols, uint32_t log_n, const uint64_t y[2][2],
+               uint32_t npoints, uint4* scratch, uint4* out) {
+    uint32_t nblocks = log_n > kEvalChunkLog ? 1u << (log_n - kEvalChunkLog) : 1;
+    dim3 grid(nblocks, ncols);
+    eval_partial_kernel<<<grid, kEvalThreads, 0, s>>>(coeff, pitch, log_n, fe_make(y[0][0], y[0][1]),
+                                                      fe_make(y[1][0], y[1][1]), npoints, scratch);
+    EZK_CUDA(cudaGetLastError());
+    uint32_t nout = ncols * npoints;
+    eval_final_kernel<<<(nout + 63) / 64, 64, 0, s>>>(scratch, nblocks, nout, out);
+    EZK_CUDA(cudaGetLastError());
+    count_launch(2);
+    return 2;
+}
+
+int deep_combine_coeffs(cudaStream_t s, const uint4* tcoeff, uint64_t tpitch, const uint4* ccoeff, uint64_t cpitch,
+                        uint32_t log_n, const uint4* deep_coeffs, uint4* pq) {
+    const uint64_t n = 1ull << log_n;
+    deep_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tcoeff, tpitch, ccoeff, cpitch, n, deep_coeffs, pq);
+    EZK_CUDA(cudaGetLastError());
+    count_launch();
+    return 1;
+}
+
+int deep_pointwise(cudaStream_t s, const uint4* root_fwd, const uint4* pq_lde, uint32_t log_L, const uint4* inv_den,
+                   DeepScalars sc, uint4* deep) {
+    const uint64_t L = 1ull << log_L;
+    deep_pointwise_kernel<<<(unsigned)((L + 255) / 256), 256, 0, s>>>(root_fwd, pq_lde, log_L, inv_den, sc, deep);
+    EZK_CUDA(cudaGetLastError());
+    count_launch();
+    return 1;
+}
+
+int check_all_zero(cudaStream_t s, const uint4* v, uint64_t count, uint32_t* flag) {
+    unsigned blocks = (unsigned)((count + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    all_zero_kernel<<<blocks, 256, 0, s>>>(v, count, flag);
+    EZK_CUDA(cudaGetLastError());
+    count_launch();
+    return 1;
+}
+
+}  // namespace ezk

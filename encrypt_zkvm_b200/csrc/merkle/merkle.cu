@@ -1,0 +1,124 @@
+// BLAKE3 row hashing + Merkle tree kernels (K3, K4).  See merkle.cuh.
+#include "merkle.cuh"
+#include "../common.h"
+#include "../hash/blake3.cuh"
+
+namespace ezk {
+
+using namespace dev;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// One thread per row; the table is column-major so a warp reads 32 consecutive 16-byte cells per column.
+__global__ void __launch_bounds__(kThreads) hash_rows_kernel(const uint4* __restrict__ table, uint64_t pitch,
+                                                            uint32_t width, uint64_t rows, uint4* __restrict__ leaves) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    uint32_t cv[8];
+    b3_init(cv);
+    const uint32_t nblocks = (width + 3) / 4;
+    for (uint32_t b = 0; b < nblocks; b++) {
+        uint32_t m[16];
+        uint32_t cells = min(4u, width - 4 * b);
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (k < cells) v = __ldg(table + (uint64_t)(4 * b + k) * pitch + i);
+            m[4 * k] = v.x, m[4 * k + 1] = v.y, m[4 * k + 2] = v.z, m[4 * k + 3] = v.w;
+        }
+        uint32_t flags = (b == 0 ? B3_CHUNK_START : 0u) | (b == nblocks - 1 ? (B3_CHUNK_END | B3_ROOT) : 0u);
+        b3_compress(cv, m, cells * 16, flags);
+    }
+    leaves[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    leaves[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+// parents k in [level, 2*level): nodes[k] = merge(nodes[2k], nodes[2k+1])
+__global__ void __launch_bounds__(kThreads) merkle_level_kernel(uint4* __restrict__ nodes, uint64_t level) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= level) return;
+    uint64_t k = level + t;
+    uint4 out[2];
+    b3_merge(nodes + 4 * k, out);  // children 2k, 2k+1 are 64 contiguous bytes at digest index 2k
+    nodes[2 * k] = out[0];
+    nodes[2 * k + 1] = out[1];
+}
+
+// finishes the tree from `level` (<= 1024 parents) down to the root inside one CTA
+__global__ void __launch_bounds__(1024) merkle_top_kernel(uint4* __restrict__ nodes, uint32_t level) {
+    for (uint32_t lvl = level; lvl >= 1; lvl >>= 1) {
+        if (threadIdx.x < lvl) {
+            uint64_t k = lvl + threadIdx.x;
+            uint4 out[2];
+            b3_merge(nodes + 4 * k, out);
+            nodes[2 * k] = out[0];
+            nodes[2 * k + 1] = out[1];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void gather_rows_kernel(const uint4* __restrict__ table, uint64_t pitch, uint32_t width,
+                                   const uint64_t* __restrict__ idx, uint32_t nq, uint4* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * width) return;
+    uint32_t q = t / width, c = t % width;
+    out[t] = table[(uint64_t)c * pitch + idx[q]];
+}
+
+__global__ void gather_digests_kernel(const uint4* __restrict__ nodes, const uint64_t* __restrict__ idx, uint32_t nq,
+                                      uint4* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    out[2 * t] = nodes[2 * idx[t]];
+    out[2 * t + 1] = nodes[2 * idx[t] + 1];
+}
+
+}  // namespace
+
+int merkle_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t rows, uint4* nodes) {
+    unsigned blocks = (unsigned)((rows + kThreads - 1) / kThreads);
+    hash_rows_kernel<<<blocks, kThreads, 0, s>>>(table, pitch, width, rows, nodes + 2 * rows);
+    EZK_CUDA(cudaGetLastError());
+    count_launch();
+    return 1;
+}
+
+int merkle_build(cudaStream_t s, uint4* nodes, uint64_t num_leaves) {
+    int launches = 0;
+    uint64_t level = num_leaves / 2;
+    for (; level > 1024; level >>= 1) {
+        unsigned blocks = (unsigned)((level + kThreads - 1) / kThreads);
+        merkle_level_kernel<<<blocks, kThreads, 0, s>>>(nodes, level);
+        EZK_CUDA(cudaGetLastError());
+        count_launch();
+        launches++;
+    }
+    if (level >= 1) {
+        merkle_top_kernel<<<1, 1024, 0, s>>>(nodes, (uint32_t)level);
+        EZK_CUDA(cudaGetLastError());
+        count_launch();
+        launches++;
+    }
+    return launches;
+}
+
+int gather_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, const uint64_t* idx, uint32_t nq,
+                uint4* out) {
+    unsigned total = nq * width;
+    gather_rows_kernel<<<(total + 127) / 128, 128, 0, s>>>(table, pitch, width, idx, nq, out);
+    EZK_CUDA(cudaGetLastError());
+    count_launch();
+    return 1;
+}
+
+int gather_digests(cudaStream_t s, const uint4* nodes, const uint64_t* idx, uint32_t nq, uint4* out) {
+    gather_digests_kernel<<<(nq + 127) / 128, 128, 0, s>>>(nodes, idx, nq, out);
+    EZK_CUDA(cudaGetLastError());
+    count_launch();
+    return 1;
+}
+
+}  // namespace ezk

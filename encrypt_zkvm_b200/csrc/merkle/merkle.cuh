@@ -1,0 +1,24 @@
+// BLAKE3 row hashing + Merkle tree construction on the GPU (kernels K3, K4 of SURVEY 8a').
+// Replaces winter-crypto's `Blake3_256::hash_elements` over LDE rows and `MerkleTree::new`, as used by
+// DefaultTraceLde::new (prover/src/lib.rs:55-62), the constraint commitment and FRI layers.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ezk {
+
+// Node array layout (same as winter-crypto): `nodes` holds 2*num_leaves digests of 32 bytes;
+// nodes[num_leaves + i] = leaf i, nodes[k] = blake3(nodes[2k] || nodes[2k+1]), nodes[1] = root.
+
+// leaf i = blake3(row i as little-endian bytes), row i = (table[c * pitch + i])_{c < width}
+int merkle_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t rows, uint4* nodes);
+// builds all internal nodes from the leaves already stored in nodes[num_leaves..2*num_leaves)
+int merkle_build(cudaStream_t s, uint4* nodes, uint64_t num_leaves);
+
+// out[q * width + c] = table[c * pitch + idx[q]]  (row gather for query openings)
+int gather_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, const uint64_t* idx, uint32_t nq,
+                uint4* out);
+// out[q] = nodes[idx[q]]  (digest gather for authentication paths)
+int gather_digests(cudaStream_t s, const uint4* nodes, const uint64_t* idx, uint32_t nq, uint4* out);
+
+}  // namespace ezk

@@ -1,0 +1,43 @@
+// Batched column NTT / coset-LDE over f128 (kernels K1, K2 of SURVEY 8a').
+// Replaces winter-math's fft::interpolate_poly / evaluate_poly_with_offset as used by
+// DefaultTraceLde::new (prover/src/lib.rs:55-62), CompositionPoly::new and the DEEP/FRI LDEs.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ezk {
+
+struct NttTables {
+    // each table: 2 * 2^14 elements (two-level powers, see f128.cuh)
+    uint4* root_fwd = nullptr;  // powers of w = primitive 2^28-th root of unity
+    uint4* root_inv = nullptr;  // powers of w^-1
+    uint4* off_fwd = nullptr;   // powers of the domain offset o = 3
+    uint4* off_inv = nullptr;   // powers of o^-1
+    int max_tile_log = 10;      // largest in-shared-memory transform (2^10 points x 8 lanes)
+};
+
+void ntt_tables_init(NttTables& t);
+void ntt_tables_free(NttTables& t);
+
+// Output scaling applied by the last pass: out[m] *= cvec[m >> chunk_shift] * (use_offset ? o^m : 1)
+struct NttScale {
+    uint64_t cvec[8][2];   // up to 8 constants {lo, hi}; cvec[0] = 1 when unused
+    uint32_t chunk_shift;  // 63 => always cvec[0]
+    uint32_t use_offset;   // 0 none, 1 multiply by o^m (forward offset table), 2 multiply by o^-m
+    uint32_t enabled;
+};
+
+// Natural-order DFT of `ncols` columns of n = 2^log_n elements: dst[c][j] = scale * sum_m src[c][m] w^(mj),
+// w = primitive n-th root (inverse root when `inverse`). `src` is left intact; `work` must hold ncols * n
+// elements when n > 2^max_tile_log (unused otherwise). src/dst pitches in elements. Returns the number of
+// kernel launches.
+int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t src_pitch, uint4* dst, uint64_t dst_pitch,
+                uint4* work, uint32_t ncols, uint32_t log_n, bool inverse, const NttScale* scale);
+
+// Coset low-degree extension with blowup 8: coeff[c][m] must already be scaled by o^m; writes
+// lde[c][8j + k] = sum_m coeff[c][m] * (w_L^k)^m * w_n^(mj)   (natural order over the LDE domain o*<w_L>).
+// tmp must hold ncols * 8 * n elements when n > 2^max_tile_log (unused otherwise).
+int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t coeff_pitch, uint4* lde,
+                uint64_t lde_pitch, uint4* tmp, uint32_t ncols, uint32_t log_n);
+
+}  // namespace ezk

@@ -1,0 +1,672 @@
+// GPU prover orchestration: one stream, device workspace, host transcript.  See prover.h.
+// Stage order follows winter-prover 0.9.0 `Prover::prove`.
+#include "prover.h"
+#include "../../include/ezkvm_prover.h"
+#include "../../include/ezkvm_rescue_constants.h"
+#include "common.h"
+#include "compose/compose.cuh"
+#include "fri/fri.cuh"
+#include "merkle/merkle.cuh"
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+
+namespace ezk {
+
+namespace {
+std::atomic<uint64_t> g_launches{0};
+
+constexpr uint32_t kWidth = 28, kCompCols = 7, kTransitions = 20, kAssertions = 22, kCycle = 16, kPeriodic = 9;
+
+inline void put(uint64_t dst[2], Fp v) {
+    dst[0] = (uint64_t)v.v;
+    dst[1] = (uint64_t)(v.v >> 64);
+}
+
+struct Pair64 {
+    uint64_t lo, hi;
+};
+const Pair64 kInvMds[16] = {EZK_RESCUE_INV_MDS_INIT};
+const Pair64 kArk[128] = {EZK_RESCUE_ARK_INIT};
+
+// interpolate 16 values over <w_16> (naive inverse DFT; 9 columns x 256 products per proof)
+std::vector<Fp> interpolate16(const Fp* values) {
+    const Fp winv = inverse(root_of_unity(4)), ninv = inverse(Fp::from_u64(16));
+    std::vector<Fp> coeffs(16);
+    for (int k = 0; k < 16; k++) {
+        Fp acc, wk = pow(winv, k), p(1);
+        for (int i = 0; i < 16; i++) {
+            acc = acc + values[i] * p;
+            p = p * wk;
+        }
+        coeffs[k] = acc * ninv;
+    }
+    return coeffs;
+}
+
+Fp horner(const std::vector<Fp>& p, Fp x) {
+    Fp acc;
+    for (size_t i = p.size(); i-- > 0;) acc = acc * x + p[i];
+    return acc;
+}
+
+}  // namespace
+
+void count_launch(uint64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+GpuProver::GpuProver(int device) : device_(device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        throw ProveFailure{EZK_ERR_NO_DEVICE, "no CUDA device available (this backend has no CPU fallback)"};
+    if (device < 0 || device >= count) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "invalid device ordinal"};
+    EZK_CUDA(cudaSetDevice(device));
+    EZK_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    ntt_tables_init(tables_);
+    pinned_bytes_ = 1 << 20;
+    EZK_CUDA(cudaMallocHost(&pinned_, pinned_bytes_));
+    EZK_CUDA(cudaMalloc(&d_params_, sizeof(ConstraintParams)));
+    EZK_CUDA(cudaMalloc(&d_flag_, sizeof(uint32_t)));
+    for (auto& e : ev_) EZK_CUDA(cudaEventCreate(&e));
+}
+
+GpuProver::~GpuProver() {
+    cudaSetDevice(device_);
+    for (auto& e : ev_) cudaEventDestroy(e);
+    cudaFree(d_flag_);
+    cudaFree(d_params_);
+    cudaFreeHost(pinned_);
+    cudaFree(arena_.base);
+    ntt_tables_free(tables_);
+    cudaStreamDestroy(stream_);
+}
+
+void GpuProver::reserve(size_t elems) {
+    if (elems <= arena_.capacity) return;
+    if (arena_.base) {
+        EZK_CUDA(cudaStreamSynchronize(stream_));
+        EZK_CUDA(cudaFree(arena_.base));
+        arena_.base = nullptr, arena_.capacity = 0;
+    }
+    last_ = Last{};
+    EZK_CUDA(cudaMalloc(&arena_.base, elems * sizeof(uint4)));
+    arena_.capacity = elems;
+}
+
+uint4* GpuProver::alloc(size_t elems) {
+    elems = (elems + 15) & ~(size_t)15;  // 256-byte granules
+    if (arena_.used + elems > arena_.capacity) throw ProveFailure{EZK_ERR_INTERNAL, "device workspace exhausted"};
+    uint4* p = arena_.base + arena_.used;
+    arena_.used += elems;
+    return p;
+}
+
+void GpuProver::sync() { EZK_CUDA(cudaStreamSynchronize(stream_)); }
+
+std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
+                                      const PublicInputs& pub, const ProofOptions& opt) {
+    if (opt.field_ext != 1) throw ProveFailure{EZK_ERR_UNSUPPORTED_FIELD_EXTENSION, "only FieldExtension::None is supported"};
+    if (opt.blowup != 8 || opt.fri_fold != 8)
+        throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "blowup factor and FRI folding factor must both be 8"};
+    if (n < 64 || (n & (n - 1)) || n > (1ull << 24))
+        throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "trace length must be a power of two in [2^6, 2^24]"};
+    if (pub.lwe_k != 4) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "the AIR requires lwe_k = 4 (lwe_size 5)"};
+    if (opt.num_queries == 0 || opt.num_queries > 255 || opt.grinding > 32 || opt.fri_rem_max_deg > 255 ||
+        ((opt.fri_rem_max_deg + 1) & opt.fri_rem_max_deg))
+        throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "unsupported proof options"};
+    EZK_CUDA(cudaSetDevice(device_));
+
+    const uint64_t L = n * 8;
+    const uint32_t log_n = ilog2_u64(n), log_L = log_n + 3;
+    const Fp o = Fp::from_u64(kDomainOffset), o_inv = inverse(o);
+    const Fp g = root_of_unity(log_n);
+    const size_t nlayers = num_fri_layers(L, opt);
+    const uint32_t eval_blocks = log_n > 14 ? 1u << (log_n - 14) : 1;
+
+    // ---- workspace ----
+    size_t fri_elems = 0;
+    {
+        uint64_t s = L;
+        for (size_t k = 0; k < nlayers; k++) {
+            fri_elems += s / 8 + 4 * (s / 8) + 64;
+            s /= 8;
+        }
+        fri_elems += 8192;
+    }
+    const size_t need = 2 * kWidth * n + 2 * kWidth * L + 4 * L + 3 * L + kCompCols * L + 4 * L + 2 * n + 2 * L + L +
+                        (size_t)(2 * kWidth + kCompCols) * eval_blocks + fri_elems + 65536;
+    reserve(need);
+    reset_arena();
+    uint4* d_trace_in = host_columns ? alloc(kWidth * n) : nullptr;
+    uint4* d_tcoef = alloc(kWidth * n);
+    uint4* d_tlde = alloc(kWidth * L);
+    uint4* d_tmp = alloc(kWidth * L);
+    uint4* d_tnodes = alloc(4 * L);
+    uint4* d_invden = alloc(L);
+    uint4* d_combined = alloc(L);
+    uint4* d_ccoef = alloc(L);
+    uint4* d_clde = alloc(kCompCols * L);
+    uint4* d_cnodes = alloc(4 * L);
+    uint4* d_pq = alloc(2 * n);
+    uint4* d_pqlde = alloc(2 * L);
+    uint4* d_deep = alloc(L);
+    uint4* d_scratch = alloc((size_t)(2 * kWidth + kCompCols) * eval_blocks);
+    uint4* d_small = alloc(4096);  // OOD outputs, deep coefficients, query staging
+    last_ = Last{};
+    last_.n = n, last_.L = L, last_.tlde = d_tlde, last_.clde = d_clde, last_.tcoef = d_tcoef;
+    last_.combined_copy = d_combined, last_.deep = d_deep;
+
+    int evi = 0;
+    auto mark = [&]() { EZK_CUDA(cudaEventRecord(ev_[evi++], stream_)); };
+    auto d2h = [&](void* dst, const void* src, size_t bytes) {
+        if (bytes > pinned_bytes_) throw ProveFailure{EZK_ERR_INTERNAL, "staging buffer too small"};
+        EZK_CUDA(cudaMemcpyAsync(pinned_, src, bytes, cudaMemcpyDeviceToHost, stream_));
+        sync();
+        memcpy(dst, pinned_, bytes);
+    };
+    auto h2d = [&](void* dst, const void* src, size_t bytes) {
+        if (bytes > pinned_bytes_) throw ProveFailure{EZK_ERR_INTERNAL, "staging buffer too small"};
+        sync();  // the staging buffer may still be in flight
+        memcpy(pinned_, src, bytes);
+        EZK_CUDA(cudaMemcpyAsync(dst, pinned_, bytes, cudaMemcpyHostToDevice, stream_));
+    };
+    auto root_of = [&](const uint4* nodes) {
+        Hash32 r;
+        d2h(r.data(), nodes + 2, 32);  // node 1
+        return r;
+    };
+
+    // ---- (0) transcript ----
+    RandomCoin coin;
+    coin.init(coin_seed(kWidth, n, opt, pub.elements));
+    std::vector<uint8_t> commitments;
+
+    // ---- (1) trace upload, interpolation, LDE, commitment ----
+    mark();
+    const uint4* d_trace = device_trace;
+    if (host_columns) {
+        for (uint32_t c = 0; c < kWidth; c++)
+            EZK_CUDA(cudaMemcpyAsync(d_trace_in + (size_t)c * n, host_columns[c], n * 16, cudaMemcpyHostToDevice, stream_));
+        d_trace = d_trace_in;
+    }
+    mark();
+    {
+        NttScale sc{};
+        put(sc.cvec[0], inverse(Fp::from_u64(n)));
+        sc.chunk_shift = 63, sc.use_offset = 1;
+        ntt_columns(tables_, stream_, d_trace, n, d_tcoef, n, d_tmp, kWidth, log_n, true, &sc);
+        lde_columns(tables_, stream_, d_tcoef, n, d_tlde, L, d_tmp, kWidth, log_n);
+    }
+    mark();
+    merkle_hash_rows(stream_, d_tlde, L, kWidth, L, d_tnodes);
+    merkle_build(stream_, d_tnodes, L);
+    last_.trace_root = root_of(d_tnodes);
+    commitments.insert(commitments.end(), last_.trace_root.begin(), last_.trace_root.end());
+    coin.reseed(last_.trace_root);
+    mark();
+
+    // ---- (2) constraint evaluation ----
+    const Fp g_last = pow(g, n - 2), g_last2 = pow(g, n - 1);
+    {
+        ConstraintParams hp{};
+        for (uint32_t j = 0; j < kTransitions; j++) put(hp.tcoef[j], coin.draw());
+        Fp bc[kAssertions];
+        for (uint32_t k = 0; k < kAssertions; k++) bc[k] = coin.draw();
+        // assertions sorted by (step, column): air/src/lib.rs:170-195 + winter-air's prepare_assertions
+        const uint32_t cols0[12] = {0, 7, 8, 11, 12, 13, 14, 15, 16, 17, 18, 19};
+        const uint32_t cols1[10] = {7, 8, 12, 13, 14, 15, 16, 17, 18, 19};
+        for (uint32_t k = 0; k < 12; k++) {
+            put(hp.bcoef[k], bc[k]);
+            put(hp.bval[k], Fp());
+            hp.bcol[k] = cols0[k];
+        }
+        for (uint32_t k = 0; k < 10; k++) {
+            put(hp.bcoef[12 + k], bc[12 + k]);
+            // values: program_hash[0..2] for columns 7,8; stack_outputs[0..8] for columns 12..19
+            put(hp.bval[12 + k], k < 2 ? pub.elements[k] : pub.elements[2 + (k - 2)]);
+            hp.bcol[12 + k] = cols1[k];
+        }
+        hp.delta = pub.lwe_delta;
+        // 1/(x^n - 1): x_i^n = o^n * w_8^(i mod 8)
+        const Fp on = pow(o, n), w8 = root_of_unity(3);
+        Fp w8c(1);
+        for (int c = 0; c < 8; c++) {
+            put(hp.inv_zn[c], inverse(on * w8c - Fp(1)));
+            w8c = w8c * w8;
+        }
+        put(hp.g_last, g_last), put(hp.g_last2, g_last2);
+        for (int i = 0; i < 16; i++) put(hp.inv_mds[i], Fp(((u128)kInvMds[i].hi << 64) | kInvMds[i].lo));
+        // periodic columns: mask + 8 ARK columns (air/src/lib.rs:201-225, rescue.rs:120-134), interpolated over
+        // <w_16> and tabulated at x^(n/16) for the 128 distinct values of step mod 128
+        std::vector<std::vector<Fp>> polys;
+        for (uint32_t p = 0; p < kPeriodic; p++) {
+            Fp vals[16];
+            for (uint32_t i = 0; i < kCycle; i++)
+                vals[i] = p == 0 ? Fp::from_u64(i < 14 ? 1 : 0)
+                                 : Fp(((u128)kArk[i * 8 + (p - 1)].hi << 64) | kArk[i * 8 + (p - 1)].lo);
+            polys.push_back(interpolate16(vals));
+        }
+        const Fp on16 = pow(o, n / kCycle), w128 = root_of_unity(7);
+        Fp wr(1);
+        for (uint32_t r = 0; r < 128; r++) {
+            const Fp y = on16 * wr;
+            for (uint32_t p = 0; p < kPeriodic; p++) put(hp.ptable[r * kPeriodic + p], horner(polys[p], y));
+            wr = wr * w128;
+        }
+        h2d(d_params_, &hp, sizeof(hp));
+        uint64_t a[2], b[2];
+        put(a, Fp(1)), put(b, g_last);
+        domain_pair_inverse(stream_, tables_.root_fwd, log_L, a, b, d_invden);
+        evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_invden, d_combined);
+    }
+    mark();
+
+    // ---- (3) composition polynomial: interpolate over the coset, 7 columns of n, LDE, commitment ----
+    {
+        NttScale sc{};
+        const Fp l_inv = inverse(Fp::from_u64(L)), o_n_inv = pow(o_inv, n);
+        Fp acc = l_inv;
+        for (int j = 0; j < 8; j++) {
+            put(sc.cvec[j], acc);  // 3^(-jn) / L
+            acc = acc * o_n_inv;
+        }
+        sc.chunk_shift = log_n, sc.use_offset = 0;
+        ntt_columns(tables_, stream_, d_combined, L, d_ccoef, L, d_tmp, 1, log_L, true, &sc);
+        EZK_CUDA(cudaMemsetAsync(d_flag_, 0, sizeof(uint32_t), stream_));
+        check_all_zero(stream_, d_ccoef + 7 * n, n, d_flag_);
+        uint32_t flag = 0;
+        d2h(&flag, d_flag_, sizeof(flag));
+        if (flag)
+            throw ProveFailure{EZK_ERR_CONSTRAINT_DEGREE,
+                               "constraint composition polynomial has degree >= 7n: the trace does not satisfy the AIR"};
+        lde_columns(tables_, stream_, d_ccoef, n, d_clde, L, d_tmp, kCompCols, log_n);
+        merkle_hash_rows(stream_, d_clde, L, kCompCols, L, d_cnodes);
+        merkle_build(stream_, d_cnodes, L);
+        last_.comp_root = root_of(d_cnodes);
+        commitments.insert(commitments.end(), last_.comp_root.begin(), last_.comp_root.end());
+        coin.reseed(last_.comp_root);
+    }
+    mark();
+
+    // ---- (4) out-of-domain frame + DEEP composition ----
+    const Fp z = coin.draw(), zg = z * g;
+    std::vector<Fp> ood_trace(2 * kWidth), ood_comp(kCompCols);  // ood_trace interleaved [cur_c, next_c]
+    {
+        uint64_t y[2][2];
+        put(y[0], z * o_inv), put(y[1], zg * o_inv);
+        uint4* d_ood = d_small;  // 56 + 7 elements
+        eval_polys(stream_, d_tcoef, n, kWidth, log_n, y, 2, d_scratch, d_ood);
+        eval_polys(stream_, d_ccoef, n, kCompCols, log_n, y, 1, d_scratch + (size_t)2 * kWidth * eval_blocks, d_ood + 2 * kWidth);
+        std::vector<Fp> host(2 * kWidth + kCompCols);
+        d2h(host.data(), d_ood, host.size() * 16);
+        std::copy(host.begin(), host.begin() + 2 * kWidth, ood_trace.begin());
+        std::copy(host.begin() + 2 * kWidth, host.end(), ood_comp.begin());
+    }
+    coin.reseed(hash_elements(ood_trace.data(), ood_trace.size()));
+    coin.reseed(hash_elements(ood_comp.data(), ood_comp.size()));
+    last_.ood_trace = ood_trace, last_.ood_comp = ood_comp;
+    {
+        std::vector<Fp> dc(kWidth + kCompCols);
+        for (auto& v : dc) v = coin.draw();
+        Fp s1, s2;
+        for (uint32_t c = 0; c < kWidth; c++) {
+            s1 = s1 + dc[c] * ood_trace[2 * c];
+            s2 = s2 + dc[c] * ood_trace[2 * c + 1];
+        }
+        for (uint32_t j = 0; j < kCompCols; j++) s1 = s1 + dc[kWidth + j] * ood_comp[j];
+        uint4* d_dc = d_small + 128;
+        h2d(d_dc, dc.data(), dc.size() * 16);
+        deep_combine_coeffs(stream_, d_tcoef, n, d_ccoef, n, log_n, d_dc, d_pq);
+        lde_columns(tables_, stream_, d_pq, n, d_pqlde, L, d_tmp, 2, log_n);
+        uint64_t a[2], b[2];
+        put(a, z), put(b, zg);
+        domain_pair_inverse(stream_, tables_.root_fwd, log_L, a, b, d_invden);
+        DeepScalars ds;
+        put(ds.z, z), put(ds.zg, zg), put(ds.s1, s1), put(ds.s2, s2);
+        deep_pointwise(stream_, tables_.root_fwd, d_pqlde, log_L, d_invden, ds, d_deep);
+    }
+    mark();
+
+    // ---- (5) FRI ----
+    struct Layer {
+        uint4* evals;
+        uint4* nodes;
+        uint64_t size;
+    };
+    std::vector<Layer> layers;
+    std::vector<Fp> remainder;
+    {
+        uint4* cur = d_deep;
+        uint64_t s = L;
+        FriFoldConsts fc{};
+        const Fp zinv = inverse(root_of_unity(3));
+        Fp zp(1);
+        for (int k = 0; k < 4; k++) {
+            put(fc.zinv[k], zp);
+            zp = zp * zinv;
+        }
+        put(fc.inv8, inverse(Fp::from_u64(8)));
+        for (size_t k = 0; k < nlayers; k++) {
+            const uint64_t m = s / 8;
+            uint4* nodes = alloc(4 * m);
+            merkle_hash_rows(stream_, cur, m, 8, m, nodes);
+            merkle_build(stream_, nodes, m);
+            Hash32 root = root_of(nodes);
+            commitments.insert(commitments.end(), root.begin(), root.end());
+            coin.reseed(root);
+            last_.fri_roots.push_back(root);
+            const Fp alpha = coin.draw();
+            put(fc.alpha_oinv, alpha * o_inv);
+            uint4* next = alloc(m);
+            fri_fold(stream_, tables_.root_inv, cur, ilog2_u64(s), fc, next);
+            layers.push_back(Layer{cur, nodes, s});
+            cur = next, s = m;
+        }
+        // remainder: interpolate the last layer over the coset; only the first s/8 coefficients may be non-zero
+        uint4* d_rem = alloc(s);
+        uint64_t inv_s[2];
+        put(inv_s, inverse(Fp::from_u64(s)));
+        fri_remainder(stream_, tables_.root_inv, tables_.off_inv, cur, ilog2_u64(s), inv_s, d_rem);
+        std::vector<Fp> all(s);
+        d2h(all.data(), d_rem, s * 16);
+        for (uint64_t i = s / 8; i < s; i++)
+            if (!all[i].is_zero())
+                throw ProveFailure{EZK_ERR_DEEP_DEGREE, "FRI remainder has degree >= domain/8: DEEP composition degree too high"};
+        remainder.assign(all.begin(), all.begin() + s / 8);
+        Hash32 commitment = hash_elements(remainder.data(), remainder.size());
+        commitments.insert(commitments.end(), commitment.begin(), commitment.end());
+        coin.reseed(commitment);
+        last_.fri_roots.push_back(commitment);
+        last_.remainder = remainder;
+    }
+    mark();
+
+    // ---- (6) grinding + query positions ----
+    uint64_t nonce = 1;
+    while (coin.leading_zeros(nonce) < opt.grinding) nonce++;
+    std::vector<uint64_t> positions = coin.draw_integers(opt.num_queries, L, nonce);
+    std::sort(positions.begin(), positions.end());
+    positions.erase(std::unique(positions.begin(), positions.end()), positions.end());
+    last_.positions = positions;
+
+    // ---- (7) openings + serialization ----
+    ProofWriter w;
+    w.u8((uint8_t)kWidth), w.u8(0), w.u8((uint8_t)log_n), w.u16(0);  // TraceInfo
+    w.u8(16);
+    w.element(Fp(Fp::modulus()));
+    w.u8((uint8_t)opt.num_queries), w.u8((uint8_t)opt.blowup), w.u8((uint8_t)opt.grinding), w.u8((uint8_t)opt.field_ext);
+    w.u8((uint8_t)opt.fri_fold), w.u8((uint8_t)opt.fri_rem_max_deg);
+    w.u8((uint8_t)positions.size());
+    w.u16((uint16_t)commitments.size());
+    w.bytes(commitments.data(), commitments.size());
+
+    uint64_t* d_idx = reinterpret_cast<uint64_t*>(alloc(8192));  // up to 16384 u64 indices
+    uint4* d_gather = alloc(32768);
+    // rows at `pos` from a column-major table + batch Merkle proof over `nodes`
+    auto write_opening = [&](const uint4* table, uint64_t pitch, uint32_t width, const uint4* nodes, uint64_t num_leaves,
+                             const std::vector<uint64_t>& pos) {
+        const uint32_t nq = (uint32_t)pos.size();
+        auto idx_lists = batch_proof_node_indices(num_leaves, pos);
+        std::vector<uint64_t> flat(pos);
+        for (auto& v : idx_lists) flat.insert(flat.end(), v.begin(), v.end());
+        const size_t ndig = flat.size() - nq;
+        if (flat.size() > 16384 || (size_t)nq * width + 2 * ndig > 32768)
+            throw ProveFailure{EZK_ERR_INTERNAL, "query staging too small"};
+        h2d(d_idx, flat.data(), flat.size() * 8);
+        gather_rows(stream_, table, pitch, width, d_idx, nq, d_gather);
+        if (ndig) gather_digests(stream_, nodes, d_idx + nq, (uint32_t)ndig, d_gather + (size_t)nq * width);
+        std::vector<uint8_t> host((size_t)nq * width * 16 + ndig * 32);
+        d2h(host.data(), d_gather, host.size());
+        const size_t vbytes = (size_t)nq * width * 16;
+        w.u32((uint32_t)vbytes);
+        w.bytes(host.data(), vbytes);
+        std::vector<uint8_t> paths;
+        paths.push_back((uint8_t)idx_lists.size());
+        const uint8_t* dg = host.data() + vbytes;
+        for (auto& v : idx_lists) {
+            paths.push_back((uint8_t)v.size());
+            paths.insert(paths.end(), dg, dg + v.size() * 32);
+            dg += v.size() * 32;
+        }
+        w.u32((uint32_t)paths.size());
+        w.bytes(paths.data(), paths.size());
+    };
+    write_opening(d_tlde, L, kWidth, d_tnodes, L, positions);
+    write_opening(d_clde, L, kCompCols, d_cnodes, L, positions);
+    // OodFrame
+    w.u16((uint16_t)(1 + ood_trace.size() * 16));
+    w.u8(2);
+    for (Fp v : ood_trace) w.element(v);
+    w.u16(1), w.u8(0);
+    w.u16((uint16_t)(ood_comp.size() * 16));
+    for (Fp v : ood_comp) w.element(v);
+    // FriProof
+    w.u8((uint8_t)nlayers);
+    {
+        std::vector<uint64_t> pos = positions;
+        for (auto& layer : layers) {
+            pos = fold_positions(pos, layer.size, 8);
+            const uint64_t m = layer.size / 8;
+            write_opening(layer.evals, m, 8, layer.nodes, m, pos);
+        }
+    }
+    w.u16((uint16_t)(remainder.size() * 16));
+    for (Fp v : remainder) w.element(v);
+    w.u8(1);
+    w.u64(nonce);
+    w.u8(0);
+    mark();
+    sync();
+    for (int i = 0; i + 1 < evi && i < 8; i++) EZK_CUDA(cudaEventElapsedTime(&stage_ms_[i], ev_[i], ev_[i + 1]));
+    return std::move(w.data());
+}
+
+std::vector<uint8_t> GpuProver::artifact(int which) {
+    EZK_CUDA(cudaSetDevice(device_));
+    auto from_device = [&](const uint4* p, size_t elems) {
+        std::vector<uint8_t> out(elems * 16);
+        if (!p) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "no proof has been generated yet"};
+        sync();
+        EZK_CUDA(cudaMemcpy(out.data(), p, out.size(), cudaMemcpyDeviceToHost));
+        return out;
+    };
+    auto from_elems = [](const std::vector<Fp>& v) {
+        return std::vector<uint8_t>((const uint8_t*)v.data(), (const uint8_t*)(v.data() + v.size()));
+    };
+    switch (which) {
+        case EZK_ART_TRACE_ROOT: return std::vector<uint8_t>(last_.trace_root.begin(), last_.trace_root.end());
+        case EZK_ART_CONSTRAINT_ROOT: return std::vector<uint8_t>(last_.comp_root.begin(), last_.comp_root.end());
+        case EZK_ART_COMBINED: return from_device(last_.combined_copy, last_.L);
+        case EZK_ART_OOD_TRACE: return from_elems(last_.ood_trace);
+        case EZK_ART_OOD_CONSTRAINTS: return from_elems(last_.ood_comp);
+        case EZK_ART_DEEP_EVALS: return from_device(last_.deep, last_.L);
+        case EZK_ART_FRI_ROOTS: {
+            std::vector<uint8_t> out;
+            for (auto& r : last_.fri_roots) out.insert(out.end(), r.begin(), r.end());
+            return out;
+        }
+        case EZK_ART_REMAINDER: return from_elems(last_.remainder);
+        case EZK_ART_POSITIONS:
+            return std::vector<uint8_t>((const uint8_t*)last_.positions.data(),
+                                        (const uint8_t*)(last_.positions.data() + last_.positions.size()));
+        case EZK_ART_TRACE_LDE: return from_device(last_.tlde, kWidth * last_.L);
+        case EZK_ART_CONSTRAINT_LDE: return from_device(last_.clde, kCompCols * last_.L);
+        case EZK_ART_TRACE_POLYS: return from_device(last_.tcoef, kWidth * last_.n);
+    }
+    throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "unknown artifact id"};
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage-level helpers
+
+void GpuProver::stage_lde(const void* columns, uint32_t width, uint64_t n, void* lde_out) {
+    if (n < 8 || (n & (n - 1)) || width == 0) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad LDE shape"};
+    EZK_CUDA(cudaSetDevice(device_));
+    const uint64_t L = 8 * n;
+    const uint32_t log_n = ilog2_u64(n);
+    reserve((size_t)width * (2 * n + 2 * L) + 1024);
+    reset_arena();
+    last_ = Last{};
+    uint4 *d_in = alloc(width * n), *d_coef = alloc(width * n), *d_lde = alloc(width * L), *d_tmp = alloc(width * L);
+    EZK_CUDA(cudaMemcpyAsync(d_in, columns, width * n * 16, cudaMemcpyHostToDevice, stream_));
+    NttScale sc{};
+    put(sc.cvec[0], inverse(Fp::from_u64(n)));
+    sc.chunk_shift = 63, sc.use_offset = 1;
+    ntt_columns(tables_, stream_, d_in, n, d_coef, n, d_tmp, width, log_n, true, &sc);
+    lde_columns(tables_, stream_, d_coef, n, d_lde, L, d_tmp, width, log_n);
+    EZK_CUDA(cudaMemcpyAsync(lde_out, d_lde, width * L * 16, cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
+
+void GpuProver::stage_ntt(const void* columns, uint32_t width, uint64_t n, bool inv, void* out) {
+    if (n < 2 || (n & (n - 1)) || width == 0) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad NTT shape"};
+    EZK_CUDA(cudaSetDevice(device_));
+    const uint32_t log_n = ilog2_u64(n);
+    reserve((size_t)width * 3 * n + 1024);
+    reset_arena();
+    last_ = Last{};
+    uint4 *d_in = alloc(width * n), *d_out = alloc(width * n), *d_tmp = alloc(width * n);
+    EZK_CUDA(cudaMemcpyAsync(d_in, columns, width * n * 16, cudaMemcpyHostToDevice, stream_));
+    NttScale sc{};
+    put(sc.cvec[0], inv ? inverse(Fp::from_u64(n)) : Fp(1));
+    sc.chunk_shift = 63, sc.use_offset = 0;
+    ntt_columns(tables_, stream_, d_in, n, d_out, n, d_tmp, width, log_n, inv, inv ? &sc : nullptr);
+    EZK_CUDA(cudaMemcpyAsync(out, d_out, width * n * 16, cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
+
+void GpuProver::stage_merkle(const void* table, uint32_t width, uint64_t rows, void* nodes_out) {
+    if (rows < 2 || (rows & (rows - 1)) || width == 0) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad Merkle shape"};
+    EZK_CUDA(cudaSetDevice(device_));
+    reserve((size_t)width * rows + 4 * rows + 1024);
+    reset_arena();
+    last_ = Last{};
+    uint4 *d_table = alloc(width * rows), *d_nodes = alloc(4 * rows);
+    EZK_CUDA(cudaMemcpyAsync(d_table, table, width * rows * 16, cudaMemcpyHostToDevice, stream_));
+    EZK_CUDA(cudaMemsetAsync(d_nodes, 0, 64, stream_));  // node 0 is unused
+    merkle_hash_rows(stream_, d_table, rows, width, rows, d_nodes);
+    merkle_build(stream_, d_nodes, rows);
+    EZK_CUDA(cudaMemcpyAsync(nodes_out, d_nodes, 2 * rows * 32, cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
+
+void GpuProver::stage_fri_fold(const void* evals, uint64_t s, Fp alpha, void* next_out) {
+    if (s < 16 || (s & (s - 1))) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad FRI layer size"};
+    EZK_CUDA(cudaSetDevice(device_));
+    reserve(s + s / 8 + 1024);
+    reset_arena();
+    last_ = Last{};
+    uint4 *d_e = alloc(s), *d_n = alloc(s / 8);
+    EZK_CUDA(cudaMemcpyAsync(d_e, evals, s * 16, cudaMemcpyHostToDevice, stream_));
+    FriFoldConsts fc{};
+    const Fp zinv = inverse(root_of_unity(3));
+    Fp zp(1);
+    for (int k = 0; k < 4; k++) {
+        put(fc.zinv[k], zp);
+        zp = zp * zinv;
+    }
+    put(fc.inv8, inverse(Fp::from_u64(8)));
+    put(fc.alpha_oinv, alpha * inverse(Fp::from_u64(kDomainOffset)));
+    fri_fold(stream_, tables_.root_inv, d_e, ilog2_u64(s), fc, d_n);
+    EZK_CUDA(cudaMemcpyAsync(next_out, d_n, (s / 8) * 16, cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
+
+void GpuProver::stage_eval_frames(const void* cur, const void* nxt, const void* periodic, uint32_t nframes, uint32_t delta,
+                                  void* out20) {
+    EZK_CUDA(cudaSetDevice(device_));
+    reserve((size_t)nframes * (28 * 2 + 9 + 20) + 1024);
+    reset_arena();
+    last_ = Last{};
+    uint4 *d_c = alloc(nframes * 28), *d_n = alloc(nframes * 28), *d_p = alloc(nframes * 9), *d_o = alloc(nframes * 20);
+    EZK_CUDA(cudaMemcpyAsync(d_c, cur, (size_t)nframes * 28 * 16, cudaMemcpyHostToDevice, stream_));
+    EZK_CUDA(cudaMemcpyAsync(d_n, nxt, (size_t)nframes * 28 * 16, cudaMemcpyHostToDevice, stream_));
+    EZK_CUDA(cudaMemcpyAsync(d_p, periodic, (size_t)nframes * 9 * 16, cudaMemcpyHostToDevice, stream_));
+    ConstraintParams hp{};
+    hp.delta = delta;
+    for (int i = 0; i < 16; i++) put(hp.inv_mds[i], Fp(((u128)kInvMds[i].hi << 64) | kInvMds[i].lo));
+    EZK_CUDA(cudaMemcpyAsync(d_params_, &hp, sizeof(hp), cudaMemcpyHostToDevice, stream_));
+    evaluate_frames(stream_, d_c, d_n, d_p, nframes, d_params_, d_o);
+    EZK_CUDA(cudaMemcpyAsync(out20, d_o, (size_t)nframes * 20 * 16, cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
+
+void GpuProver::bench_lde_merkle(uint32_t width, uint64_t n, int iters, float* lde_ms, float* merkle_ms) {
+    if (n < 8 || (n & (n - 1)) || width == 0 || iters < 1) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad shape"};
+    EZK_CUDA(cudaSetDevice(device_));
+    const uint64_t L = 8 * n;
+    const uint32_t log_n = ilog2_u64(n);
+    reserve((size_t)width * (2 * n + 2 * L) + 4 * L + 1024);
+    reset_arena();
+    last_ = Last{};
+    uint4 *d_in = alloc(width * n), *d_coef = alloc(width * n), *d_lde = alloc(width * L), *d_tmp = alloc(width * L);
+    uint4* d_nodes = alloc(4 * L);
+    // synthetic column data: any byte pattern below the modulus will do (top word cleared)
+    EZK_CUDA(cudaMemsetAsync(d_in, 0x5A, width * n * 16, stream_));
+    NttScale sc{};
+    put(sc.cvec[0], inverse(Fp::from_u64(n)));
+    sc.chunk_shift = 63, sc.use_offset = 1;
+    float t_lde = 0, t_mk = 0;
+    for (int it = -1; it < iters; it++) {  // iteration -1 is a warm-up
+        EZK_CUDA(cudaEventRecord(ev_[0], stream_));
+        ntt_columns(tables_, stream_, d_in, n, d_coef, n, d_tmp, width, log_n, true, &sc);
+        lde_columns(tables_, stream_, d_coef, n, d_lde, L, d_tmp, width, log_n);
+        EZK_CUDA(cudaEventRecord(ev_[1], stream_));
+        merkle_hash_rows(stream_, d_lde, L, width, L, d_nodes);
+        merkle_build(stream_, d_nodes, L);
+        EZK_CUDA(cudaEventRecord(ev_[2], stream_));
+        sync();
+        float a, b;
+        EZK_CUDA(cudaEventElapsedTime(&a, ev_[0], ev_[1]));
+        EZK_CUDA(cudaEventElapsedTime(&b, ev_[1], ev_[2]));
+        if (it >= 0) t_lde += a, t_mk += b;
+    }
+    *lde_ms = t_lde / iters, *merkle_ms = t_mk / iters;
+}
+
+void GpuProver::bench_fri(uint64_t n, int iters, float* fri_ms) {
+    if (n < 64 || (n & (n - 1)) || iters < 1) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad shape"};
+    EZK_CUDA(cudaSetDevice(device_));
+    const uint64_t L = 8 * n;
+    ProofOptions opt;
+    const size_t nlayers = num_fri_layers(L, opt);
+    reserve(L + L + 1024);
+    reset_arena();
+    last_ = Last{};
+    uint4* d_e = alloc(L);
+    EZK_CUDA(cudaMemsetAsync(d_e, 0x5A, L * 16, stream_));
+    FriFoldConsts fc{};
+    const Fp zinv = inverse(root_of_unity(3));
+    Fp zp(1);
+    for (int k = 0; k < 4; k++) {
+        put(fc.zinv[k], zp);
+        zp = zp * zinv;
+    }
+    put(fc.inv8, inverse(Fp::from_u64(8)));
+    put(fc.alpha_oinv, Fp::from_u64(0x123456789ULL));
+    const size_t mark0 = arena_.used;
+    float total = 0;
+    for (int it = -1; it < iters; it++) {
+        arena_.used = mark0;
+        uint4* cur = d_e;
+        uint64_t s = L;
+        EZK_CUDA(cudaEventRecord(ev_[0], stream_));
+        for (size_t k = 0; k < nlayers; k++) {
+            const uint64_t m = s / 8;
+            uint4* nodes = alloc(4 * m);
+            merkle_hash_rows(stream_, cur, m, 8, m, nodes);
+            merkle_build(stream_, nodes, m);
+            uint4* next = alloc(m);
+            fri_fold(stream_, tables_.root_inv, cur, ilog2_u64(s), fc, next);
+            cur = next, s = m;
+        }
+        EZK_CUDA(cudaEventRecord(ev_[1], stream_));
+        sync();
+        float a;
+        EZK_CUDA(cudaEventElapsedTime(&a, ev_[0], ev_[1]));
+        if (it >= 0) total += a;
+    }
+    *fri_ms = total / iters;
+}
+
+}  // namespace ezk

@@ -1,0 +1,78 @@
+// GPU prover: everything `winterfell::Prover::prove` does after trace generation, on one B200.
+// Drop-in for `ExecutionProver::prove` (prover/src/lib.rs:40-77, called at vm/src/lib.rs:26).
+#pragma once
+#include "air/constraints.cuh"
+#include "host/transcript.h"
+#include "ntt/ntt.cuh"
+#include <string>
+#include <vector>
+
+namespace ezk {
+
+struct ProveFailure {
+    int code;  // ezk_status
+    std::string message;
+};
+
+struct PublicInputs {
+    Fp elements[18];  // program_hash[2] ++ stack_outputs[16]   (air/src/lib.rs:38-47)
+    uint32_t lwe_k = 4, lwe_delta = 16;
+};
+
+class GpuProver {
+public:
+    explicit GpuProver(int device);
+    ~GpuProver();
+    GpuProver(const GpuProver&) = delete;
+
+    // host columns (28 pointers) or device-resident trace; exactly one of them non-null
+    std::vector<uint8_t> prove(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
+                               const PublicInputs& pub, const ProofOptions& opt);
+
+    const float* stage_ms() const { return stage_ms_; }
+    std::vector<uint8_t> artifact(int which);
+
+    // stage-level helpers (host buffers)
+    void stage_lde(const void* columns, uint32_t width, uint64_t n, void* lde_out);
+    void stage_ntt(const void* columns, uint32_t width, uint64_t n, bool inverse, void* out);
+    void stage_merkle(const void* table, uint32_t width, uint64_t rows, void* nodes_out);
+    void stage_fri_fold(const void* evals, uint64_t s, Fp alpha, void* next_out);
+    void stage_eval_frames(const void* cur, const void* nxt, const void* periodic, uint32_t nframes, uint32_t delta,
+                           void* out20);
+    void bench_lde_merkle(uint32_t width, uint64_t n, int iters, float* lde_ms, float* merkle_ms);
+    void bench_fri(uint64_t n, int iters, float* fri_ms);
+
+private:
+    struct Arena {
+        uint4* base = nullptr;
+        size_t capacity = 0, used = 0;  // in 16-byte units
+    };
+    uint4* alloc(size_t elems);
+    void reserve(size_t elems);
+    void reset_arena() { arena_.used = 0; }
+    void sync();
+
+    int device_;
+    cudaStream_t stream_ = nullptr;
+    NttTables tables_;
+    Arena arena_;
+    uint8_t* pinned_ = nullptr;  // small host staging buffer
+    size_t pinned_bytes_ = 0;
+    ConstraintParams* d_params_ = nullptr;
+    uint32_t* d_flag_ = nullptr;
+    cudaEvent_t ev_[16];
+    float stage_ms_[8] = {0};
+
+    // state of the last proof (device pointers into the arena + host copies), for ezk_prover_artifact
+    struct Last {
+        uint64_t n = 0, L = 0;
+        uint4 *tlde = nullptr, *clde = nullptr, *tcoef = nullptr, *combined_copy = nullptr, *deep = nullptr;
+        Hash32 trace_root{}, comp_root{};
+        std::vector<Fp> ood_trace, ood_comp, remainder;
+        std::vector<Hash32> fri_roots;
+        std::vector<uint64_t> positions;
+        bool keep_combined = false;
+    } last_;
+};
+
+}  // namespace ezk

@@ -1,0 +1,179 @@
+/* C ABI of the B200 proving backend for Encrypt-zkVM.
+ *
+ * Drop-in boundary: `prover.prove(trace)` at vm/src/lib.rs:26, i.e. the `winterfell::Prover` implementation
+ * `ExecutionProver` of prover/src/lib.rs:17-77 (BaseField f128, ProcessorAir, Blake3_256, DefaultRandomCoin,
+ * DefaultTraceLde, DefaultConstraintEvaluator).  The reference has no FFI of its own (pure Rust, no unsafe);
+ * these are the entry points a Rust shim would bind (see INTEGRATION.md for the `extern "C"` block).
+ *
+ * All field elements cross the boundary as 16 little-endian bytes of the canonical u128 value - exactly the
+ * memory of `winterfell::math::fields::f128::BaseElement`, so a `&[BaseElement]` can be passed as a pointer.
+ * Every function returns EZK_OK (0) or a negative error code; ezk_last_error() gives the message (thread-local).
+ * The library never falls back to the CPU: without a CUDA device every compute entry point fails with
+ * EZK_ERR_NO_DEVICE.
+ */
+#ifndef EZKVM_PROVER_H
+#define EZKVM_PROVER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EZK_TRACE_WIDTH 28 /* vm/src/processor/mod.rs:76-84 */
+
+enum ezk_status {
+    EZK_OK = 0,
+    EZK_ERR_INVALID_ARGUMENT = -1,
+    EZK_ERR_UNSUPPORTED_FIELD_EXTENSION = -2, /* ProverError::UnsupportedFieldExtension */
+    EZK_ERR_CONSTRAINT_DEGREE = -3,           /* ProverError::MismatchedConstraintPolynomialDegree: trace violates the AIR */
+    EZK_ERR_DEEP_DEGREE = -4,                 /* winterfell's assert on the DEEP polynomial degree / FRI remainder */
+    EZK_ERR_NO_DEVICE = -5,
+    EZK_ERR_CUDA = -6,
+    EZK_ERR_VM = -7,                          /* ProgramError / ProcessorError (message mirrors the reference's Display) */
+    EZK_ERR_INTERNAL = -8
+};
+
+/* winterfell::ProofOptions::new(32, 8, 0, FieldExtension::None, 8, 127) - vm/src/lib.rs:20 */
+typedef struct ezk_options {
+    uint32_t num_queries;              /* 32 */
+    uint32_t blowup_factor;            /* 8 (the only supported value) */
+    uint32_t grinding_factor;          /* 0 */
+    uint32_t field_extension;          /* 1 = FieldExtension::None (the only supported value) */
+    uint32_t fri_folding_factor;       /* 8 (the only supported value) */
+    uint32_t fri_remainder_max_degree; /* 127 */
+} ezk_options;
+
+/* air::PublicInputs (air/src/lib.rs:18-47) + the two ServerKey parameters the AIR reads
+ * (fhe/src/parameters.rs:4-21, used at air/src/constrains.rs:113,129-130,151). */
+typedef struct ezk_public_inputs {
+    uint8_t program_hash[2][16];
+    uint8_t stack_outputs[16][16];
+    uint32_t lwe_k;     /* must be 4: the AIR hard-codes lwe_size 5 (constrains.rs:104-105,175) */
+    uint32_t lwe_delta; /* ciphertext_modulus / plaintext_modulus */
+} ezk_public_inputs;
+
+/* TraceTable<BaseElement> (vm/src/lib.rs:18): `width` column pointers, each `length` elements of 16 bytes. */
+typedef struct ezk_trace {
+    const uint8_t* const* columns;
+    uint32_t width;  /* 28 */
+    uint64_t length; /* power of two, >= 64 */
+} ezk_trace;
+
+typedef struct ezk_prover ezk_prover; /* holds the CUDA stream, twiddle tables and a reusable device workspace */
+
+/* ---- library ---- */
+const char* ezk_last_error(void);
+const char* ezk_version(void);
+int ezk_device_count(void);           /* number of visible CUDA devices (0 without a GPU; never fails) */
+uint64_t ezk_kernel_launch_count(void); /* kernels launched by this library since load */
+void ezk_free(void* p);               /* frees buffers returned by this library */
+void ezk_default_options(ezk_options* out);
+
+/* ---- prover object: ExecutionProver::new (prover/src/lib.rs:25-37) ---- */
+int ezk_prover_create(int device, ezk_prover** out);
+void ezk_prover_destroy(ezk_prover* p);
+
+/* ExecutionProver::prove (prover/src/lib.rs:40-77 via winterfell::Prover::prove): host trace in, serialized
+ * `winterfell::Proof` bytes out (`Proof::to_bytes` layout).  *proof is malloc'ed; release with ezk_free. */
+int ezk_prover_prove(ezk_prover* p, const ezk_trace* trace, const ezk_public_inputs* pub, const ezk_options* opt,
+                     uint8_t** proof, size_t* proof_len);
+/* Same, with the trace already resident in device memory as 28 contiguous columns (column c at
+ * d_trace + c * length * 16).  The buffer is not modified. */
+int ezk_prover_prove_device(ezk_prover* p, const void* d_trace, uint64_t length, const ezk_public_inputs* pub,
+                            const ezk_options* opt, uint8_t** proof, size_t* proof_len);
+/* One-shot convenience with a lazily created default prover on device 0 (what a Rust shim calls). */
+int ezk_prove(const ezk_trace* trace, const ezk_public_inputs* pub, const ezk_options* opt, uint8_t** proof,
+              size_t* proof_len);
+
+/* Device-time of the stages of the last proof, milliseconds (CUDA events on the prover's stream). */
+enum ezk_stage {
+    EZK_STAGE_UPLOAD = 0,     /* host -> device trace copy */
+    EZK_STAGE_TRACE_LDE,      /* 28 x iNTT + coset LDE          (DefaultTraceLde::new) */
+    EZK_STAGE_TRACE_COMMIT,   /* BLAKE3 rows + Merkle tree */
+    EZK_STAGE_CONSTRAINTS,    /* divisor inverses + fused AIR evaluation (DefaultConstraintEvaluator) */
+    EZK_STAGE_COMPOSITION,    /* iNTT(8n) + 7 LDEs + commitment */
+    EZK_STAGE_DEEP,           /* OOD evaluation + DEEP composition + LDE */
+    EZK_STAGE_FRI,            /* layers + remainder */
+    EZK_STAGE_QUERIES,        /* openings + proof assembly */
+    EZK_STAGE_COUNT
+};
+int ezk_prover_stage_times(const ezk_prover* p, float* ms_out /* EZK_STAGE_COUNT */);
+
+/* Intermediate values of the last proof, for stage-by-stage parity tests. Copies up to `cap` bytes into dst and
+ * returns the full size in *size_out (call with dst = NULL to query). Elements are 16 LE bytes, digests 32. */
+enum ezk_artifact {
+    EZK_ART_TRACE_ROOT = 0,
+    EZK_ART_CONSTRAINT_ROOT,
+    EZK_ART_COMBINED,         /* L constraint evaluations */
+    EZK_ART_OOD_TRACE,        /* 56 elements, interleaved cur/next */
+    EZK_ART_OOD_CONSTRAINTS,  /* 7 elements */
+    EZK_ART_DEEP_EVALS,       /* L elements */
+    EZK_ART_FRI_ROOTS,        /* (layers + 1) digests, last = remainder commitment */
+    EZK_ART_REMAINDER,        /* remainder coefficients */
+    EZK_ART_POSITIONS,        /* u64 query positions (sorted, unique) */
+    EZK_ART_TRACE_LDE,        /* column-major 28 x L */
+    EZK_ART_CONSTRAINT_LDE,   /* column-major 7 x L */
+    EZK_ART_TRACE_POLYS,      /* column-major 28 x n coefficients, scaled by 3^m */
+    EZK_ART_COUNT
+};
+int ezk_prover_artifact(ezk_prover* p, int which, void* dst, size_t cap, size_t* size_out);
+
+/* ---- stage-level entry points (host buffers in/out; used by parity tests and the stage sweep) ---- */
+/* Column-major `width` x n values -> column-major `width` x 8n LDE over the coset 3*<w_8n> (iNTT + coset NTT). */
+int ezk_stage_lde(ezk_prover* p, const void* columns, uint32_t width, uint64_t n, void* lde_out);
+/* Column-major `width` x rows table -> 2*rows digests (node k at 32*k; node 1 = root; leaves from `rows`). */
+int ezk_stage_merkle(ezk_prover* p, const void* table, uint32_t width, uint64_t rows, void* nodes_out);
+/* FRI over evaluations on 3*<w_s>: returns (layers+1) roots, the remainder coefficients and the folded layers.
+ * alphas come from the caller (one per layer) so the stage is testable without a transcript. */
+int ezk_stage_fri_fold(ezk_prover* p, const void* evals, uint64_t s, const void* alpha16, void* next_out);
+/* 20 transition-constraint values for explicit frames (reference unit tests: air/src/tests/mod.rs). */
+int ezk_stage_eval_frames(ezk_prover* p, const void* cur, const void* next, const void* periodic, uint32_t nframes,
+                          uint32_t lwe_delta, void* out20);
+/* Plain transform of column-major `width` x n values; inverse != 0 -> interpolation (scaled by 1/n). */
+int ezk_stage_ntt(ezk_prover* p, const void* columns, uint32_t width, uint64_t n, int inverse, void* out);
+/* Device-resident stage benchmarks for the LDE/Merkle/FRI sweep: run `iters` times on synthetic device data,
+ * return the average device time per iteration in milliseconds. */
+int ezk_bench_lde_merkle(ezk_prover* p, uint32_t width, uint64_t n, int iters, float* lde_ms, float* merkle_ms);
+int ezk_bench_fri(ezk_prover* p, uint64_t n, int iters, float* fri_ms);
+
+/* ---- host VM (vm crate restated; stays on the host per the north star) ---- */
+typedef struct ezk_program ezk_program;
+typedef struct ezk_execution ezk_execution;
+
+/* Program::compile (vm/src/program/mod.rs:37-96). On error returns EZK_ERR_VM and ezk_last_error() holds
+ * "program error at {step}: {message}" exactly as the reference formats it. */
+int ezk_program_compile(const char* source, ezk_program** out);
+void ezk_program_free(ezk_program* p);
+size_t ezk_program_len(const ezk_program* p);
+void ezk_program_ops(const ezk_program* p, uint8_t* codes, uint8_t* values);
+void ezk_program_hash(const ezk_program* p, uint8_t out[2][16]);
+/* Display impl: "push(1) noop ..." ; returns bytes needed (incl. NUL), writes at most cap. */
+size_t ezk_program_display(const ezk_program* p, char* dst, size_t cap);
+
+/* Processor::run + Processor::trace (vm/src/processor/mod.rs:61-95). secret: num_ciphertexts * (lwe_k+1) elements.
+ * The last trace row is filled from SplitMix64(last_row_seed) instead of thread_rng. */
+int ezk_vm_execute(const ezk_program* prog, const uint8_t* public_tape, size_t public_len, const void* secret_elems,
+                   size_t num_ciphertexts, uint32_t lwe_k, uint32_t lwe_delta, uint64_t last_row_seed,
+                   ezk_execution** out);
+void ezk_execution_free(ezk_execution* e);
+uint64_t ezk_execution_length(const ezk_execution* e);
+const uint8_t* ezk_execution_column(const ezk_execution* e, uint32_t c); /* length * 16 bytes */
+void ezk_execution_outputs(const ezk_execution* e, uint8_t out[16][16]);
+
+/* Synthetic benchmark programs: kind 1 scalar, 2 ciphertext, 3 mixed. Produces the
+ * program, its tapes and the executed trace of length 2^log_n. */
+int ezk_synthetic_case(int kind, uint32_t log_n, uint32_t lwe_k, uint32_t lwe_delta, uint64_t seed, ezk_program** prog,
+                       ezk_execution** exec);
+
+/* LWE client side with a seeded PRNG (fhe/src/server_key.rs:19-76): key = k elements, ciphertext = k+1. */
+void ezk_lwe_keygen(uint32_t k, uint64_t seed, void* key_out);
+void ezk_lwe_encrypt(const void* key, uint32_t k, uint32_t delta, double std_dev, uint8_t value, uint64_t seed,
+                     void* ct_out);
+uint8_t ezk_lwe_decrypt(const void* key, uint32_t k, uint32_t delta, const void* ct);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EZKVM_PROVER_H */
