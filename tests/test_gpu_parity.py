@@ -1,0 +1,198 @@
+"""GPU parity tests: every CUDA stage and the whole proof against the CPU oracle, through the C ABI.
+
+Bar: bit-exact (all arithmetic on this path is integer / byte work).  Sizes are chosen so the oracle finishes
+in seconds; larger sizes are covered by size-independent properties in test_gpu_properties.py.
+"""
+import numpy as np
+import pytest
+
+from tests import _oracle
+from tests._cases import lr_case, small_case, synthetic, pub_elements
+
+pytestmark = pytest.mark.gpu
+
+M = _oracle.MODULUS
+
+
+def rand_elems(rng, shape):
+    """uniform canonical field elements as uint64 (.., 2) words"""
+    lo = rng.integers(0, 2**64, size=shape, dtype=np.uint64)
+    hi = rng.integers(0, 2**64 - 1, size=shape, dtype=np.uint64)  # hi < 2^64-1  =>  value < M
+    return np.stack([lo, hi], axis=-1)
+
+
+@pytest.fixture(scope="module")
+def prover(gpu_prover_factory):
+    ezk = gpu_prover_factory
+    p = ezk.ExecutionProver(ezk.ProofOptions(), [0, 0], [0] * 16, ezk.ServerKey())
+    yield p
+    p.close()
+
+
+@pytest.mark.parametrize("log_n", [1, 3, 6, 9, 10, 11, 13, 16])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_ntt_matches_oracle(prover, oracle, log_n, inverse):
+    rng = np.random.default_rng(100 + log_n)
+    n = 1 << log_n
+    cols = rand_elems(rng, (3, n))
+    got = prover.stage_ntt(cols, inverse)
+    for c in range(3):
+        want = oracle.interpolate(cols[c]) if inverse else oracle.forward_ntt(cols[c])
+        assert np.array_equal(got[c], want), f"column {c}"
+
+
+@pytest.mark.parametrize("log_n,width", [(3, 1), (6, 28), (7, 7), (9, 5), (10, 28), (11, 3), (12, 28), (14, 2), (16, 1)])
+def test_lde_matches_oracle(prover, oracle, log_n, width):
+    rng = np.random.default_rng(200 + log_n)
+    n = 1 << log_n
+    cols = rand_elems(rng, (width, n))
+    got = prover.stage_lde(cols)
+    for c in range(width):
+        _, want = oracle.lde_column(cols[c])
+        assert np.array_equal(got[c], want), f"column {c}"
+
+
+@pytest.mark.parametrize("rows,width", [(2, 1), (16, 28), (512, 7), (4096, 8), (1 << 14, 28), (1 << 15, 3)])
+def test_merkle_matches_oracle(prover, oracle, rows, width):
+    rng = np.random.default_rng(300 + rows)
+    table = rand_elems(rng, (width, rows))  # column-major, as the GPU keeps it
+    got = prover.stage_merkle(table)
+    root, nodes = oracle.merkle_rows(np.ascontiguousarray(table.transpose(1, 0, 2)))
+    assert got[32:64] == root
+    assert got[32:] == nodes[32:]
+
+
+@pytest.mark.parametrize("log_s", [4, 10, 13, 16])
+def test_fri_fold_matches_formula(prover, oracle, log_s):
+    """e'[i] = sum_k (alpha/x_i)^k (1/8) sum_j e[i + j m] zeta^(-jk), x_i = 3 w_s^i."""
+    rng = np.random.default_rng(400 + log_s)
+    s = 1 << log_s
+    m = s // 8
+    evals = rand_elems(rng, (s,))
+    alpha = int(rng.integers(1, 2**62)) * 0x1234567 % M
+    got = _oracle.from_arr(prover.stage_fri_fold(evals, alpha))
+    e = _oracle.from_arr(evals)
+    w = oracle.root_of_unity(log_s)
+    zeta_inv = pow(oracle.root_of_unity(3), M - 2, M)
+    inv8, inv3 = pow(8, M - 2, M), pow(3, M - 2, M)
+    idx = list(range(0, m, max(1, m // 64)))[:64] + [m - 1]
+    for i in idx:
+        xinv = inv3 * pow(w, (M - 1 - i) % (M - 1), M) % M
+        acc = 0
+        for k in range(8):
+            sk = sum(e[i + j * m] * pow(zeta_inv, j * k, M) for j in range(8)) % M
+            acc = (acc + sk * inv8 % M * pow(alpha * xinv % M, k, M)) % M
+        assert got[i] == acc, i
+
+
+def _check_full_proof(ezk, oracle, trace, program_hash, outputs, delta=16, options=None, min_security=95):
+    pub = pub_elements(program_hash, outputs)
+    opt = options or ezk.ProofOptions()
+    oopt = _oracle.default_options(delta=delta, num_queries=opt.num_queries, grinding=opt.grinding_factor,
+                                   fri_rem_max_deg=opt.fri_remainder_max_degree)
+    want = oracle.prove(trace, pub, oopt)
+    params = ezk.LweParameters(plaintext_modulus=8, ciphertext_modulus=8 * delta)
+    with ezk.ExecutionProver(opt, program_hash, outputs, ezk.ServerKey(params)) as p:
+        proof = p.prove(trace)
+        n = trace.shape[1]
+        L = 8 * n
+        # stage by stage, in pipeline order, so the first divergence is the one reported
+        tl = np.frombuffer(p.artifact("trace_lde"), dtype=np.uint64).reshape(28, L, 2)
+        want_tl = want.array("trace_lde").reshape(L, 28, 2).transpose(1, 0, 2)
+        assert np.array_equal(tl, want_tl), "trace LDE"
+        assert p.artifact("trace_root") == want.raw("trace_root"), "trace root"
+        assert p.artifact("combined") == want.raw("combined"), "constraint evaluations"
+        cl = np.frombuffer(p.artifact("constraint_lde"), dtype=np.uint64).reshape(7, L, 2)
+        want_cl = want.array("comp_lde").reshape(L, 7, 2).transpose(1, 0, 2)
+        assert np.array_equal(cl, want_cl), "composition LDE"
+        assert p.artifact("constraint_root") == want.raw("comp_root"), "constraint root"
+        ood = _oracle.from_arr(np.frombuffer(p.artifact("ood_trace"), dtype=np.uint64))
+        assert ood[0::2] == want.elements("ood_cur") and ood[1::2] == want.elements("ood_next"), "OOD trace frame"
+        assert p.artifact("ood_constraints") == want.raw("ood_comp"), "OOD constraint evaluations"
+        assert p.artifact("deep_evals") == want.raw("deep_evals"), "DEEP evaluations"
+        assert p.artifact("fri_roots") == want.raw("fri_roots"), "FRI layer roots"
+        assert p.artifact("remainder") == want.raw("remainder"), "FRI remainder"
+        assert p.artifact("positions") == want.raw("positions"), "query positions"
+    assert proof.to_bytes() == want.proof, "serialized proof bytes"
+    assert oracle.verify(proof.to_bytes(), pub, oopt, min_security) == 0, "oracle verifier rejects the GPU proof"
+    return proof
+
+
+def test_prove_linear_regression_example(gpu_prover_factory, oracle):
+    """configs[0]: examples/linear_regression (lr.txt, n = 128, 0 FRI layers)."""
+    case = lr_case()
+    _check_full_proof(gpu_prover_factory, oracle, case.trace, case.program_hash, case.outputs)
+
+
+def test_prove_reference_unit_test_program(gpu_prover_factory, oracle):
+    """vm/src/lib.rs:47-99 `test_prove`: read2 read sadd push.1 push.2 add smul (n = 128 after padding)."""
+    case = small_case()
+    _check_full_proof(gpu_prover_factory, oracle, case.trace, case.program_hash, case.outputs)
+
+
+@pytest.mark.parametrize("kind,log_n", [(1, 7), (2, 8), (3, 9), (1, 10), (2, 11), (3, 12), (2, 13), (1, 14)])
+def test_prove_synthetic_matches_oracle(gpu_prover_factory, oracle, kind, log_n):
+    case = synthetic(kind, log_n)
+    assert case.trace.shape[1] == 1 << log_n
+    _check_full_proof(gpu_prover_factory, oracle, case.trace, case.program_hash, case.outputs)
+
+
+def test_prove_other_options_and_delta(gpu_prover_factory, oracle):
+    ezk = gpu_prover_factory
+    case = synthetic(3, 10, delta=32)
+    opt = ezk.ProofOptions(num_queries=20, grinding_factor=8, fri_remainder_max_degree=31)
+    # 20 queries * 3 bits + 8 grinding bits - 1 = 67 bits of conjectured security
+    _check_full_proof(ezk, oracle, case.trace, case.program_hash, case.outputs, delta=32, options=opt, min_security=67)
+
+
+def test_prove_device_resident_trace_gives_same_bytes(gpu_prover_factory, oracle):
+    import torch
+    ezk = gpu_prover_factory
+    case = synthetic(2, 10)
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        host = p.prove(case.trace).to_bytes()
+        d = torch.from_numpy(case.trace.view(np.int64)).to("cuda:0")
+        torch.cuda.synchronize()
+        dev = p.prove_device(d.data_ptr(), case.trace.shape[1]).to_bytes()
+        again = p.prove(case.trace).to_bytes()
+    assert host == dev == again
+
+
+def test_invalid_trace_is_rejected(gpu_prover_factory):
+    """A trace violating the AIR must fail loudly (winterfell: MismatchedConstraintPolynomialDegree / debug asserts)."""
+    ezk = gpu_prover_factory
+    case = synthetic(1, 8)
+    bad = case.trace.copy()
+    bad[12, 5, 0] ^= np.uint64(1)  # flip one stack cell
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        with pytest.raises(ezk.ProverError) as ei:
+            p.prove(bad)
+        assert ei.value.code in (-3, -4)
+
+
+def test_argument_errors(gpu_prover_factory):
+    ezk = gpu_prover_factory
+    case = synthetic(1, 7)
+    with ezk.ExecutionProver(ezk.ProofOptions(field_extension=2), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        with pytest.raises(ezk.ProverError) as ei:
+            p.prove(case.trace)
+        assert ei.value.code == -2  # UnsupportedFieldExtension
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        with pytest.raises(ezk.ProverError):
+            p.prove(case.trace[:, :96])  # not a power of two
+
+
+def test_air_frames_on_gpu_match_oracle(prover, oracle):
+    """The reference's AIR unit-test frames (air/src/tests/mod.rs) + random frames: 20 values, bit-exact."""
+    from tests._frames import reference_frames
+    rng = np.random.default_rng(7)
+    frames = reference_frames()
+    cur = [f.cur for f in frames] + [_oracle.from_arr(rand_elems(rng, (28,))) for _ in range(64)]
+    nxt = [f.nxt for f in frames] + [_oracle.from_arr(rand_elems(rng, (28,))) for _ in range(64)]
+    per = [f.periodic for f in frames] + [_oracle.from_arr(rand_elems(rng, (9,))) for _ in range(64)]
+    for delta in (16, 4096):
+        got = prover.stage_eval_frames(np.stack([_oracle.to_arr(c) for c in cur]), np.stack([_oracle.to_arr(c) for c in nxt]),
+                                       np.stack([_oracle.to_arr(c) for c in per]), delta)
+        for k in range(len(cur)):
+            want = oracle.evaluate_transition(cur[k], nxt[k], per[k], delta=delta)
+            assert _oracle.from_arr(got[k]) == want, f"frame {k}"
