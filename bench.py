@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the trace -> proof path (BASELINE.json metric: proofs/sec at a 2^20-row trace).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log-n 20] [--kind 2]
+
+One "step" = one full proof of the synthetic ciphertext program (READ2/READ/SMUL/ADD2/SADD, BASELINE.md
+config 2) padded to 2^log_n trace rows.  Prints ONE JSON line (rank 0).
+
+* value     : proofs/s with the trace already resident in HBM (ezk_prover_prove_device), device-timed with CUDA
+              events on the prover's stream, max over ranks.  N > 1: every rank proves its own trace on its own
+              GPU (independent proofs, no data-path collective) -> weak scaling.
+* e2e       : the same metric through the host-buffer C-ABI call (ezk_prover_prove): pinned host trace in,
+              proof bytes out, copies inside the timed region.
+* roofline  : dominant kernel of the timed region (per-kernel CUDA events inside the library).
+* cpu_baseline / --impl reference : the CPU oracle (restated reference path) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "proofs_per_sec"
+UNIT = "proofs/s"
+CPU_SAMPLE_LOG_N = 16
+
+
+def algo_bytes_per_proof(n: int) -> dict:
+    """Minimum compulsory HBM traffic per stage with unfused stages (BASELINE.md / SURVEY 8d), bytes."""
+    return {"trace_lde": 4032 * n, "trace_commit": 4352 * n, "constraints": 3712 * n, "composition": 2928 * n,
+            "deep": 1280 * n, "fri": 274 * n}
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])), smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_run(log_n: int, kind: int, threads: int, repeats: int = 1):
+    """Times the CPU oracle's prove() on a bounded sample; returns (seconds per proof, threads used)."""
+    import encrypt_zkvm_b200 as ezk
+    from tests import _oracle
+    o = _oracle.load()
+    o.lib.orc_set_num_threads(threads)
+    prog, ex = ezk.synthetic_case(kind, log_n)
+    trace, pub = ex.trace(), prog.hash() + ex.outputs()
+    best = None
+    for _ in range(repeats):
+        art = o.prove(trace, pub)
+        best = art.seconds if best is None else min(best, art.seconds)
+    return best, threads
+
+
+def scale_to_full(seconds_sample: float, sample_log_n: int, log_n: int) -> float:
+    """proofs/s at 2^log_n extrapolated from a 2^sample_log_n sample with the n*log2(n) work model."""
+    factor = (2 ** (log_n - sample_log_n)) * (log_n / sample_log_n)
+    return 1.0 / (seconds_sample * factor)
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's own CPU implementation of the path.  The Rust prover cannot be built here
+    (no cargo/rustc, winterfell 0.9.0 not vendored), so this arm times the CPU oracle - the restated reference
+    algorithm - with all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = min(CPU_SAMPLE_LOG_N, args.log_n)
+    for _ in range(args.warmup and 1):  # one warm-up proof is enough for a CPU run that takes seconds
+        cpu_oracle_run(sample, args.kind, threads)
+    t0 = time.perf_counter()
+    secs = []
+    for _ in range(args.steps):
+        s, _ = cpu_oracle_run(sample, args.kind, threads)
+        secs.append(s)
+    wall = time.perf_counter() - t0
+    per = sum(secs) / len(secs)
+    value = scale_to_full(per, sample, args.log_n)
+    sample_txt = (f"oracle prove of the same synthetic program at 2^{sample} rows: {per:.2f} s/proof on {threads} threads "
+                  f"(OpenMP); scaled to 2^{args.log_n} rows by n*log2(n) (x{2 ** (args.log_n - sample) * args.log_n / sample:.1f})")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u128 (f128 field) + u32 (BLAKE3)", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args) -> dict:
+    kinds = {1: "scalar PUSH/READ/ADD/MUL", 2: "ciphertext READ2/READ/SMUL/ADD2/SADD", 3: "mixed"}
+    return {"workload": f"synthetic {kinds[args.kind]} program padded to 2^{args.log_n} trace rows, 28 columns, "
+                        f"blowup 8, 32 queries, FRI folding 8 (BASELINE.json configs[2])",
+            "trace_rows": 1 << args.log_n, "lde_rows": 8 << args.log_n, "field": "f128", "hash": "blake3-256",
+            "parallelism": f"{args.gpus} independent provers (one per GPU)" if args.gpus > 1 else "1 GPU",
+            "l2": "inputs larger than L2 (trace 28*n*16 B, LDE 8x that)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--kind", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import encrypt_zkvm_b200 as ezk
+
+    if ezk.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device visible; this backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- workload: host VM builds the trace (north star: trace generation stays on the host) ----
+    n = 1 << args.log_n
+    prog, ex = ezk.synthetic_case(args.kind, args.log_n, seed=0xE2C0DE00 + args.log_n + 1000 * rank)
+    trace_np = ex.trace()
+    program_hash, outputs = prog.hash(), ex.outputs()
+    host = torch.from_numpy(trace_np.view(np.int64)).pin_memory()      # (28, n, 2) pinned
+    host_np = host.numpy().view(np.uint64)
+    dev = host.to(f"cuda:{local_rank}", non_blocking=False)            # resident copy for the `value` arm
+    del trace_np, ex
+    h2d_bytes = 28 * n * 16
+
+    prover = ezk.ExecutionProver(ezk.ProofOptions(), program_hash, outputs, ezk.ServerKey(), device=local_rank)
+
+    # ---- device-resident arm ----
+    for _ in range(max(args.warmup, 3)):
+        proof = prover.prove_device(dev.data_ptr(), n)
+    sampler = ClockSampler(local_rank)
+    ezk.profile_enable(True)
+    ezk.profile_reset()
+    barrier()
+    launches0 = ezk.kernel_launch_count()
+    sampler.start()
+    prover.timer_start()
+    for _ in range(args.steps):
+        proof = prover.prove_device(dev.data_ptr(), n)
+    ms = prover.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = ezk.kernel_launch_count() - launches0
+    profile = ezk.profile_read()
+    ezk.profile_enable(False)
+    stage_ms = prover.stage_times_ms()
+    t_dev = max_over_ranks(ms / 1e3)
+    value = world * args.steps / t_dev
+
+    # ---- end-to-end arm: pinned host trace in, proof bytes out ----
+    for _ in range(2):
+        proof = prover.prove(host_np)
+    barrier()
+    prover.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        proof = prover.prove(host_np)
+    ms_e2e_dev = prover.timer_stop()
+    wall_e2e = time.perf_counter() - t0
+    barrier()
+    t_e2e = max_over_ranks(max(ms_e2e_dev / 1e3, wall_e2e))
+    e2e_value = world * args.steps / t_e2e
+    proof_bytes = len(proof)
+    launches_total = int(sum_over_ranks(float(launches)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (device time from CUDA events around every launch) ----
+    peak, peak_kind = hbm_peak()
+    top = max(profile.items(), key=lambda kv: kv[1]["ms"]) if profile else None
+    roofline = None
+    if top:
+        name, st = top
+        achieved = st["algo_bytes"] / (st["ms"] * 1e-3) / 1e9 if st["ms"] > 0 else 0.0
+        traffic = None
+        tf = ROOT / "profiles" / "roofline_traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get(name)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "peak_source": peak_kind,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "launches_per_step": st["launches"] / args.steps,
+                    "avg_launch_ms": st["ms"] / st["launches"],
+                    "algo_bytes_per_launch": st["algo_bytes"] / st["launches"],
+                    "share_of_step": st["ms"] / (ms if ms else 1.0)}
+    kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                   "GBps": (v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
+               for k, v in sorted(profile.items(), key=lambda kv: -kv[1]["ms"])}
+    ab = algo_bytes_per_proof(n)
+    stages = {k: {"ms": stage_ms[k], "GBps": (ab[k] / (stage_ms[k] * 1e-3) / 1e9) if k in ab and stage_ms[k] > 0 else None,
+                  "frac_of_hbm_peak": (ab[k] / (stage_ms[k] * 1e-3) / 1e9 / peak) if k in ab and stage_ms[k] > 0 else None}
+              for k in stage_ms}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle, single thread like the reference's configuration ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample = min(CPU_SAMPLE_LOG_N, args.log_n)
+        secs, threads = cpu_oracle_run(sample, args.kind, 1)
+        cpu = {"value": scale_to_full(secs, sample, args.log_n), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"oracle prove of the same synthetic program at 2^{sample} rows: {secs:.2f} s on 1 thread (the "
+                         f"reference runs Winterfell single-threaded); scaled to 2^{args.log_n} rows by n*log2(n)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_dev * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u128 (f128 field) + u32 (BLAKE3)", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": proof_bytes,
+                "ms_per_step": t_e2e * 1e3 / args.steps},
+        "gpu_launches": launches_total, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "stages": stages, "kernels": kernels, "proof_bytes": proof_bytes,
+        "hbm_roofline_proofs_per_s": peak * 1e9 / sum(ab.values()),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,13 @@ SIGNATURES = {
     "ezk_prove": (C.c_int, [C.POINTER(EzkTrace), C.POINTER(EzkPublicInputs), C.POINTER(EzkOptions), C.POINTER(_P),
                             C.POINTER(C.c_size_t)]),
     "ezk_prover_stage_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "ezk_prover_timer_start": (C.c_int, [_P]),
+    "ezk_prover_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "ezk_profile_enable": (None, [C.c_int]),
+    "ezk_profile_reset": (None, []),
+    "ezk_profile_kernel_count": (C.c_int, []),
+    "ezk_profile_kernel_name": (C.c_char_p, [C.c_int]),
+    "ezk_profile_read": (None, [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "ezk_prover_artifact": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ezk_stage_lde": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, _P]),
     "ezk_stage_merkle": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, _P]),

@@ -127,9 +127,11 @@ int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, uint32_t log_L, c
     const unsigned threads = 128;
     uint64_t need = (L + kBatch - 1) / kBatch;
     unsigned blocks = (unsigned)((need + threads - 1) / threads);
-    pair_inverse_kernel<<<blocks, threads, 0, s>>>(root_fwd, log_L, fe_make(a[0], a[1]), fe_make(b[0], b[1]), out);
+    {
+        LaunchScope ls(s, K_PAIR_INVERSE, L * 16);
+        pair_inverse_kernel<<<blocks, threads, 0, s>>>(root_fwd, log_L, fe_make(a[0], a[1]), fe_make(b[0], b[1]), out);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 
@@ -137,18 +139,22 @@ int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde
                          const ConstraintParams* params, const uint4* inv_den, uint4* combined) {
     const uint64_t L = 1ull << log_L;
     const unsigned threads = 128;
-    constraint_kernel<<<(unsigned)((L + threads - 1) / threads), threads, 0, s>>>(root_fwd, lde, pitch, log_L, params,
-                                                                                inv_den, combined);
+    {
+        LaunchScope ls(s, K_CONSTRAINTS, L * 16 * (28 + 2));  // 28 columns + inv_den read, 1 column written
+        constraint_kernel<<<(unsigned)((L + threads - 1) / threads), threads, 0, s>>>(root_fwd, lde, pitch, log_L, params,
+                                                                                    inv_den, combined);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 
 int evaluate_frames(cudaStream_t s, const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,
                     const ConstraintParams* params, uint4* out) {
-    frames_kernel<<<(nframes + 63) / 64, 64, 0, s>>>(cur, nxt, periodic, nframes, params, out);
+    {
+        LaunchScope ls(s, K_FRAMES, (uint64_t)nframes * 16 * (28 * 2 + 9 + 20));
+        frames_kernel<<<(nframes + 63) / 64, 64, 0, s>>>(cur, nxt, periodic, nframes, params, out);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 

@@ -151,6 +151,26 @@ int ezk_prover_stage_times(const ezk_prover* p, float* ms_out) {
     });
 }
 
+int ezk_prover_timer_start(ezk_prover* p) {
+    return guarded([&] {
+        if (!p) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        p->impl->timer_start();
+    });
+}
+int ezk_prover_timer_stop(ezk_prover* p, float* ms_out) {
+    return guarded([&] {
+        if (!p || !ms_out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        *ms_out = p->impl->timer_stop();
+    });
+}
+void ezk_profile_enable(int on) { profile_enable(on != 0); }
+void ezk_profile_reset(void) { profile_reset(); }
+int ezk_profile_kernel_count(void) { return K_COUNT; }
+const char* ezk_profile_kernel_name(int kernel) { return kernel_name(kernel); }
+void ezk_profile_read(int kernel, uint64_t* launches, double* ms, uint64_t* algo_bytes) {
+    profile_read(kernel, launches, ms, algo_bytes);
+}
+
 int ezk_prover_artifact(ezk_prover* p, int which, void* dst, size_t cap, size_t* size_out) {
     return guarded([&] {
         if (!p) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};

@@ -101,40 +101,51 @@ int eval_polys(cudaStream_t s, const uint4* coeff, uint64_t pitch, uint32_t ncol
                uint32_t npoints, uint4* scratch, uint4* out) {
     uint32_t nblocks = log_n > kEvalChunkLog ? 1u << (log_n - kEvalChunkLog) : 1;
     dim3 grid(nblocks, ncols);
-    eval_partial_kernel<<<grid, kEvalThreads, 0, s>>>(coeff, pitch, log_n, fe_make(y[0][0], y[0][1]),
-                                                      fe_make(y[1][0], y[1][1]), npoints, scratch);
+    {
+        LaunchScope ls(s, K_EVAL_POLYS, ((uint64_t)ncols << log_n) * 16);
+        eval_partial_kernel<<<grid, kEvalThreads, 0, s>>>(coeff, pitch, log_n, fe_make(y[0][0], y[0][1]),
+                                                          fe_make(y[1][0], y[1][1]), npoints, scratch);
+    }
     EZK_CUDA(cudaGetLastError());
     uint32_t nout = ncols * npoints;
-    eval_final_kernel<<<(nout + 63) / 64, 64, 0, s>>>(scratch, nblocks, nout, out);
+    {
+        LaunchScope ls(s, K_EVAL_POLYS, (uint64_t)nout * nblocks * 16);
+        eval_final_kernel<<<(nout + 63) / 64, 64, 0, s>>>(scratch, nblocks, nout, out);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch(2);
     return 2;
 }
 
 int deep_combine_coeffs(cudaStream_t s, const uint4* tcoeff, uint64_t tpitch, const uint4* ccoeff, uint64_t cpitch,
                         uint32_t log_n, const uint4* deep_coeffs, uint4* pq) {
     const uint64_t n = 1ull << log_n;
-    deep_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tcoeff, tpitch, ccoeff, cpitch, n, deep_coeffs, pq);
+    {
+        LaunchScope ls(s, K_DEEP_COMBINE, n * 16 * (35 + 2));
+        deep_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tcoeff, tpitch, ccoeff, cpitch, n, deep_coeffs, pq);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 
 int deep_pointwise(cudaStream_t s, const uint4* root_fwd, const uint4* pq_lde, uint32_t log_L, const uint4* inv_den,
                    DeepScalars sc, uint4* deep) {
     const uint64_t L = 1ull << log_L;
-    deep_pointwise_kernel<<<(unsigned)((L + 255) / 256), 256, 0, s>>>(root_fwd, pq_lde, log_L, inv_den, sc, deep);
+    {
+        LaunchScope ls(s, K_DEEP_POINTWISE, L * 16 * 4);
+        deep_pointwise_kernel<<<(unsigned)((L + 255) / 256), 256, 0, s>>>(root_fwd, pq_lde, log_L, inv_den, sc, deep);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 
 int check_all_zero(cudaStream_t s, const uint4* v, uint64_t count, uint32_t* flag) {
     unsigned blocks = (unsigned)((count + 255) / 256);
     if (blocks > 1184) blocks = 1184;
-    all_zero_kernel<<<blocks, 256, 0, s>>>(v, count, flag);
+    {
+        LaunchScope ls(s, K_ALL_ZERO, count * 16);
+        all_zero_kernel<<<blocks, 256, 0, s>>>(v, count, flag);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 

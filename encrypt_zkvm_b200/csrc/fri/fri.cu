@@ -82,18 +82,22 @@ __global__ void fri_remainder_kernel(const uint4* __restrict__ root_inv, const u
 
 int fri_fold(cudaStream_t s, const uint4* root_inv, const uint4* evals, uint32_t log_s, FriFoldConsts c, uint4* next) {
     const uint64_t m = 1ull << (log_s - 3);
-    fri_fold_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(root_inv, evals, log_s, c, next);
+    {
+        LaunchScope ls(s, K_FRI_FOLD, m * 16 * 9);
+        fri_fold_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(root_inv, evals, log_s, c, next);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 
 int fri_remainder(cudaStream_t s, const uint4* root_inv, const uint4* off_inv, const uint4* evals, uint32_t log_s,
                   const uint64_t inv_s[2], uint4* coeffs) {
     const uint32_t n = 1u << log_s;
-    fri_remainder_kernel<<<(n + 63) / 64, 64, 0, s>>>(root_inv, off_inv, evals, log_s, fe_make(inv_s[0], inv_s[1]), coeffs);
+    {
+        LaunchScope ls(s, K_FRI_REMAINDER, (uint64_t)n * 32);
+        fri_remainder_kernel<<<(n + 63) / 64, 64, 0, s>>>(root_inv, off_inv, evals, log_s, fe_make(inv_s[0], inv_s[1]), coeffs);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 

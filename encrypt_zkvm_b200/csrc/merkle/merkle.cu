@@ -80,9 +80,11 @@ __global__ void gather_digests_kernel(const uint4* __restrict__ nodes, const uin
 
 int merkle_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t rows, uint4* nodes) {
     unsigned blocks = (unsigned)((rows + kThreads - 1) / kThreads);
-    hash_rows_kernel<<<blocks, kThreads, 0, s>>>(table, pitch, width, rows, nodes + 2 * rows);
+    {
+        LaunchScope ls(s, K_HASH_ROWS, rows * ((uint64_t)width * 16 + 32));
+        hash_rows_kernel<<<blocks, kThreads, 0, s>>>(table, pitch, width, rows, nodes + 2 * rows);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 
@@ -91,15 +93,19 @@ int merkle_build(cudaStream_t s, uint4* nodes, uint64_t num_leaves) {
     uint64_t level = num_leaves / 2;
     for (; level > 1024; level >>= 1) {
         unsigned blocks = (unsigned)((level + kThreads - 1) / kThreads);
-        merkle_level_kernel<<<blocks, kThreads, 0, s>>>(nodes, level);
+        {
+            LaunchScope ls(s, K_MERKLE_LEVEL, level * 96);
+            merkle_level_kernel<<<blocks, kThreads, 0, s>>>(nodes, level);
+        }
         EZK_CUDA(cudaGetLastError());
-        count_launch();
         launches++;
     }
     if (level >= 1) {
-        merkle_top_kernel<<<1, 1024, 0, s>>>(nodes, (uint32_t)level);
+        {
+            LaunchScope ls(s, K_MERKLE_TOP, level * 2 * 96);
+            merkle_top_kernel<<<1, 1024, 0, s>>>(nodes, (uint32_t)level);
+        }
         EZK_CUDA(cudaGetLastError());
-        count_launch();
         launches++;
     }
     return launches;
@@ -108,16 +114,20 @@ int merkle_build(cudaStream_t s, uint4* nodes, uint64_t num_leaves) {
 int gather_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, const uint64_t* idx, uint32_t nq,
                 uint4* out) {
     unsigned total = nq * width;
-    gather_rows_kernel<<<(total + 127) / 128, 128, 0, s>>>(table, pitch, width, idx, nq, out);
+    {
+        LaunchScope ls(s, K_GATHER, (uint64_t)total * 32);
+        gather_rows_kernel<<<(total + 127) / 128, 128, 0, s>>>(table, pitch, width, idx, nq, out);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 
 int gather_digests(cudaStream_t s, const uint4* nodes, const uint64_t* idx, uint32_t nq, uint4* out) {
-    gather_digests_kernel<<<(nq + 127) / 128, 128, 0, s>>>(nodes, idx, nq, out);
+    {
+        LaunchScope ls(s, K_GATHER, (uint64_t)nq * 64);
+        gather_digests_kernel<<<(nq + 127) / 128, 128, 0, s>>>(nodes, idx, nq, out);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return 1;
 }
 

@@ -243,9 +243,14 @@ int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log
         a.log_L = log_L;
         a.roots = roots;
         dim3 grid((unsigned)(((uint64_t)1 << (log_n - pl.log_d[i])) / kLanes), ncols);
-        ntt_strided_pass<<<grid, kThreads, tile_bytes(pl.log_d[i], kLanes, false), s>>>(a);
+        {
+            // compulsory traffic: every element of every column read once and written once (the 8 coset copies of
+            // an LDE first pass share one read of the coefficient column)
+            const uint64_t elems = (uint64_t)ncols << log_n;
+            LaunchScope ls(s, K_NTT_STRIDED, (a.coset_first ? elems / 8 + elems : 2 * elems) * 16);
+            ntt_strided_pass<<<grid, kThreads, tile_bytes(pl.log_d[i], kLanes, false), s>>>(a);
+        }
         EZK_CUDA(cudaGetLastError());
-        count_launch();
         launches++;
     }
     (void)t;
@@ -317,9 +322,11 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
     }
     uint64_t runs = 1ull << (log_n - pl.log_d[0]);
     dim3 grid((unsigned)(pl.passes >= 2 ? runs / kLanes : 1), ncols);
-    ntt_final_pass<<<grid, kThreads, tile_bytes(pl.log_d[0], 1u << a.lanes_log, true), s>>>(a);
+    {
+        LaunchScope ls(s, K_NTT_FINAL, ((uint64_t)ncols << log_n) * 32);
+        ntt_final_pass<<<grid, kThreads, tile_bytes(pl.log_d[0], 1u << a.lanes_log, true), s>>>(a);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return launches + 1;
 }
 
@@ -347,9 +354,12 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
         a.src = tmp, a.src_pitch = n;
     }
     dim3 grid((unsigned)(1ull << (log_n - pl.log_d[0])), ncols);
-    ntt_final_pass<<<grid, kThreads, tile_bytes(pl.log_d[0], 8, true), s>>>(a);
+    {
+        const uint64_t elems = (uint64_t)ncols << log_n;
+        LaunchScope ls(s, K_NTT_FINAL, (pl.passes == 1 ? elems + 8 * elems : 16 * elems) * 16);
+        ntt_final_pass<<<grid, kThreads, tile_bytes(pl.log_d[0], 8, true), s>>>(a);
+    }
     EZK_CUDA(cudaGetLastError());
-    count_launch();
     return launches + 1;
 }
 

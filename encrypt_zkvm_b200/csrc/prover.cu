@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <mutex>
 
 namespace ezk {
 
@@ -55,6 +56,63 @@ Fp horner(const std::vector<Fp>& p, Fp x) {
 void count_launch(uint64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+namespace {
+struct ProfileSlot {
+    cudaEvent_t start, stop;
+    int id;
+    uint64_t bytes;
+};
+struct Profiler {
+    bool enabled = false;
+    std::vector<ProfileSlot> slots;
+    size_t used = 0;
+    std::mutex mu;
+} g_prof;
+const char* const kKernelNames[K_COUNT] = {"ntt_strided_pass", "ntt_final_pass", "hash_rows", "merkle_level", "merkle_top",
+                                            "gather", "pair_inverse", "constraints", "frames", "eval_polys", "deep_combine",
+                                            "deep_pointwise", "all_zero", "fri_fold", "fri_remainder"};
+}  // namespace
+
+const char* kernel_name(int id) { return id >= 0 && id < K_COUNT ? kKernelNames[id] : "?"; }
+void profile_enable(bool on) { g_prof.enabled = on; }
+void profile_reset() {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    g_prof.used = 0;
+}
+void profile_read(int id, uint64_t* launches, double* ms, uint64_t* algo_bytes) {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    cudaDeviceSynchronize();
+    uint64_t n = 0, b = 0;
+    double t = 0;
+    for (size_t i = 0; i < g_prof.used; i++) {
+        if (g_prof.slots[i].id != id) continue;
+        float e = 0;
+        if (cudaEventElapsedTime(&e, g_prof.slots[i].start, g_prof.slots[i].stop) == cudaSuccess) t += e;
+        n++, b += g_prof.slots[i].bytes;
+    }
+    if (launches) *launches = n;
+    if (ms) *ms = t;
+    if (algo_bytes) *algo_bytes = b;
+}
+
+LaunchScope::LaunchScope(cudaStream_t s, KernelId id, uint64_t algo_bytes) : stream(s), slot(-1) {
+    count_launch();
+    if (!g_prof.enabled) return;
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    if (g_prof.used == g_prof.slots.size()) {
+        ProfileSlot ps{};
+        if (cudaEventCreate(&ps.start) != cudaSuccess || cudaEventCreate(&ps.stop) != cudaSuccess) return;
+        g_prof.slots.push_back(ps);
+    }
+    slot = (int)g_prof.used++;
+    g_prof.slots[slot].id = id;
+    g_prof.slots[slot].bytes = algo_bytes;
+    cudaEventRecord(g_prof.slots[slot].start, stream);
+}
+LaunchScope::~LaunchScope() {
+    if (slot >= 0) cudaEventRecord(g_prof.slots[slot].stop, stream);
+}
+
 GpuProver::GpuProver(int device) : device_(device) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
@@ -68,11 +126,26 @@ GpuProver::GpuProver(int device) : device_(device) {
     EZK_CUDA(cudaMalloc(&d_params_, sizeof(ConstraintParams)));
     EZK_CUDA(cudaMalloc(&d_flag_, sizeof(uint32_t)));
     for (auto& e : ev_) EZK_CUDA(cudaEventCreate(&e));
+    for (auto& e : timer_ev_) EZK_CUDA(cudaEventCreate(&e));
+}
+
+void GpuProver::timer_start() {
+    EZK_CUDA(cudaSetDevice(device_));
+    EZK_CUDA(cudaEventRecord(timer_ev_[0], stream_));
+}
+float GpuProver::timer_stop() {
+    EZK_CUDA(cudaSetDevice(device_));
+    EZK_CUDA(cudaEventRecord(timer_ev_[1], stream_));
+    EZK_CUDA(cudaEventSynchronize(timer_ev_[1]));
+    float ms = 0;
+    EZK_CUDA(cudaEventElapsedTime(&ms, timer_ev_[0], timer_ev_[1]));
+    return ms;
 }
 
 GpuProver::~GpuProver() {
     cudaSetDevice(device_);
     for (auto& e : ev_) cudaEventDestroy(e);
+    for (auto& e : timer_ev_) cudaEventDestroy(e);
     cudaFree(d_flag_);
     cudaFree(d_params_);
     cudaFreeHost(pinned_);

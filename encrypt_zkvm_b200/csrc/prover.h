@@ -30,6 +30,8 @@ public:
                                const PublicInputs& pub, const ProofOptions& opt);
 
     const float* stage_ms() const { return stage_ms_; }
+    void timer_start();
+    float timer_stop();
     std::vector<uint8_t> artifact(int which);
 
     // stage-level helpers (host buffers)
@@ -61,6 +63,7 @@ private:
     ConstraintParams* d_params_ = nullptr;
     uint32_t* d_flag_ = nullptr;
     cudaEvent_t ev_[16];
+    cudaEvent_t timer_ev_[2];
     float stage_ms_[8] = {0};
 
     // state of the last proof (device pointers into the arena + host copies), for ezk_prover_artifact

@@ -183,6 +183,15 @@ class ExecutionProver:
                                          C.byref(out), C.byref(out_len))
         return self._finish(rc, out, out_len)
 
+    # -- timing -----------------------------------------------------------------------------------------
+    def timer_start(self) -> None:
+        check(lib.ezk_prover_timer_start(self._handle))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        check(lib.ezk_prover_timer_stop(self._handle, C.byref(ms)))
+        return ms.value
+
     # -- introspection ----------------------------------------------------------------------------------
     def stage_times_ms(self) -> dict:
         ms = (C.c_float * len(_lib.STAGES))()
@@ -245,6 +254,25 @@ class ExecutionProver:
         a = C.c_float()
         check(lib.ezk_bench_fri(self._handle, n, iters, C.byref(a)))
         return a.value
+
+
+def profile_enable(on: bool) -> None:
+    lib.ezk_profile_enable(int(on))
+
+
+def profile_reset() -> None:
+    lib.ezk_profile_reset()
+
+
+def profile_read() -> dict:
+    """kernel name -> {launches, ms, algo_bytes} since the last reset (CUDA events around every launch)."""
+    out = {}
+    for k in range(lib.ezk_profile_kernel_count()):
+        n, ms, b = C.c_uint64(), C.c_double(), C.c_uint64()
+        lib.ezk_profile_read(k, C.byref(n), C.byref(ms), C.byref(b))
+        if n.value:
+            out[lib.ezk_profile_kernel_name(k).decode()] = {"launches": n.value, "ms": ms.value, "algo_bytes": b.value}
+    return out
 
 
 def device_count() -> int:

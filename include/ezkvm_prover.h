@@ -101,6 +101,19 @@ enum ezk_stage {
 };
 int ezk_prover_stage_times(const ezk_prover* p, float* ms_out /* EZK_STAGE_COUNT */);
 
+/* Brackets any sequence of calls with CUDA events on the prover's stream (device-side wall time, includes the
+ * host transcript gaps between kernels): start, run, stop -> milliseconds. */
+int ezk_prover_timer_start(ezk_prover* p);
+int ezk_prover_timer_stop(ezk_prover* p, float* ms_out);
+
+/* Per-kernel profile (CUDA events around every launch; off by default). */
+void ezk_profile_enable(int on);
+void ezk_profile_reset(void);
+int ezk_profile_kernel_count(void);
+const char* ezk_profile_kernel_name(int kernel);
+/* totals since the last reset: launches, summed device milliseconds, summed algorithmic bytes */
+void ezk_profile_read(int kernel, uint64_t* launches, double* ms, uint64_t* algo_bytes);
+
 /* Intermediate values of the last proof, for stage-by-stage parity tests. Copies up to `cap` bytes into dst and
  * returns the full size in *size_out (call with dst = NULL to query). Elements are 16 LE bytes, digests 32. */
 enum ezk_artifact {

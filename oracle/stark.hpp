@@ -407,6 +407,14 @@ static inline void prove(const u128* const* cols, size_t n, const u128* pub18, c
     {
         std::vector<u128> tnum(L), b0(L), b1(L), d0(L), d1(L), dz(L);
         auto xs = power_table(wL, L);
+        std::vector<u128> zn_minus_1(B);
+        {
+            u128 on = fexp(o, n), wB = root_of_unity(ilog2(B)), acc = 1;
+            for (size_t c = 0; c < B; c++) {
+                zn_minus_1[c] = fsub(fmul(on, acc), 1);
+                acc = fmul(acc, wB);
+            }
+        }
 #pragma omp parallel for schedule(static)
         for (size_t i = 0; i < L; i++) {
             u128 x = fmul(o, xs[i]);
@@ -418,7 +426,7 @@ static inline void prove(const u128* const* cols, size_t n, const u128* pub18, c
             for (unsigned j = 0; j < NUM_TRANSITION; j++) t = fadd(t, fmul(A.tcoef[j], ev[j]));
             // transition divisor (x^n - 1) / ((x - g^(n-2)) (x - g^(n-1)))
             tnum[i] = fmul(t, fmul(fsub(x, g_last), fsub(x, g_last2)));
-            dz[i] = fsub(fexp(x, n), 1);
+            dz[i] = zn_minus_1[i % B];  // x^n - 1 takes only B distinct values: x^n = o^n * w_B^(i mod B)
             u128 s0 = 0, s1 = 0;
             for (unsigned k = 0; k < NUM_ASSERTIONS; k++) {
                 u128 term = fmul(A.bcoef[k], fsub(cur[asserts[k].column], asserts[k].value));
