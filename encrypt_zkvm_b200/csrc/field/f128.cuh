@@ -1,8 +1,14 @@
 // Device arithmetic in the reference's base field f128: M = 2^128 - 45*2^40 + 1
 // (`winterfell::math::fields::f128::BaseElement`, prover/src/lib.rs:4,41).
 // Elements are canonical (< M), 16 little-endian bytes in memory, moved with 128-bit loads/stores.
-// 2^128 = 45*2^40 - 1 (mod M), so a 256-bit product folds with one multiply-by-45, shifts and adds;
-// no tensor cores: this is 32-bit integer-pipe work (IMAD.WIDE + IADD3 carry chains).
+//
+// No tensor cores: this is 32-bit integer-pipe work.  An element is four 32-bit limbs; the 256-bit product is
+// accumulated in even/odd 64-bit columns so that every partial product is ONE IMAD.WIDE.U32 with carry-in/out
+// (mad.lo.cc + madc.hi.cc pairs, which ptxas fuses), 16 of them per product.  The fold uses
+//     2^128 = 45*2^40 - 1 = 11520*2^32 - 1 (mod M):
+// hi*2^128 = (hi*11520) << 32 - hi, a limb-aligned shift, so the reduction is 4 more IMAD.WIDE and two
+// carry chains, then a second tiny fold of the < 2^46 overflow.  ~58 SASS instructions per modmul
+// (checked with cuobjdump), against ~120 for the 64-bit-limb formulation it replaces.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -11,166 +17,238 @@ namespace ezk {
 namespace dev {
 
 struct fe {
-    uint64_t lo, hi;
+    uint32_t a0, a1, a2, a3;
 };
 
 #define EZK_MOD_LO 0xFFFFD30000000001ULL
 #define EZK_MOD_HI 0xFFFFFFFFFFFFFFFFULL
+#define EZK_M1 0xFFFFD300u  // limb 1 of M (limb 0 = 1, limbs 2,3 = all ones)
+#define EZK_K1 0x00002CFFu  // limb 1 of K = 2^128 - M = 45*2^40 - 1 (limb 0 = all ones, limbs 2,3 = 0)
 
 __host__ __device__ __forceinline__ fe fe_make(uint64_t lo, uint64_t hi = 0) {
     fe r;
-    r.lo = lo, r.hi = hi;
+    r.a0 = (uint32_t)lo, r.a1 = (uint32_t)(lo >> 32), r.a2 = (uint32_t)hi, r.a3 = (uint32_t)(hi >> 32);
     return r;
 }
 __device__ __forceinline__ fe fe_zero() { return fe_make(0, 0); }
 __device__ __forceinline__ fe fe_one() { return fe_make(1, 0); }
-__device__ __forceinline__ bool fe_is_zero(fe a) { return (a.lo | a.hi) == 0; }
-__device__ __forceinline__ bool fe_eq(fe a, fe b) { return a.lo == b.lo && a.hi == b.hi; }
+__device__ __forceinline__ bool fe_is_zero(fe a) { return (a.a0 | a.a1 | a.a2 | a.a3) == 0; }
+__device__ __forceinline__ bool fe_eq(fe a, fe b) { return a.a0 == b.a0 && a.a1 == b.a1 && a.a2 == b.a2 && a.a3 == b.a3; }
 
-__device__ __forceinline__ fe fe_load(const uint4* p) {
-    uint4 v = *p;
-    return fe_make(((uint64_t)v.y << 32) | v.x, ((uint64_t)v.w << 32) | v.z);
+__device__ __forceinline__ fe fe_from(uint4 v) {
+    fe r;
+    r.a0 = v.x, r.a1 = v.y, r.a2 = v.z, r.a3 = v.w;
+    return r;
 }
-__device__ __forceinline__ fe fe_ldg(const uint4* p) {
-    uint4 v = __ldg(p);
-    return fe_make(((uint64_t)v.y << 32) | v.x, ((uint64_t)v.w << 32) | v.z);
+__device__ __forceinline__ uint4 fe_to(fe a) { return make_uint4(a.a0, a.a1, a.a2, a.a3); }
+__device__ __forceinline__ fe fe_load(const uint4* p) { return fe_from(*p); }
+__device__ __forceinline__ fe fe_ldg(const uint4* p) { return fe_from(__ldg(p)); }
+__device__ __forceinline__ void fe_store(uint4* p, fe a) { *p = fe_to(a); }
+
+// s += K (i.e. -M mod 2^128), dropping the carry
+__device__ __forceinline__ void fe_add_k(fe& s) {
+    asm("add.cc.u32 %0, %0, 0xFFFFFFFF;\n\t"
+        "addc.cc.u32 %1, %1, 0x2CFF;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.u32 %3, %3, 0;"
+        : "+r"(s.a0), "+r"(s.a1), "+r"(s.a2), "+r"(s.a3));
 }
-__device__ __forceinline__ void fe_store(uint4* p, fe a) {
-    uint4 v;
-    v.x = (uint32_t)a.lo, v.y = (uint32_t)(a.lo >> 32), v.z = (uint32_t)a.hi, v.w = (uint32_t)(a.hi >> 32);
-    *p = v;
+
+// Rarely taken tail of add / mul: `ov` = the value wrapped past 2^128 once; then canonicalise (s >= M -> s - M).
+static __device__ __noinline__ fe fe_fix_rare(fe s, uint32_t ov) {
+    if (ov) fe_add_k(s);
+    if (s.a3 == 0xFFFFFFFFu && s.a2 == 0xFFFFFFFFu && (s.a1 > EZK_M1 || (s.a1 == EZK_M1 && s.a0 >= 1u))) fe_add_k(s);
+    return s;
 }
 
 // r = a + b (mod M), canonical inputs -> canonical output
 __device__ __forceinline__ fe fe_add(fe a, fe b) {
-    uint64_t lo, hi, c;
-    asm("add.cc.u64 %0, %3, %5;\n\t"
-        "addc.cc.u64 %1, %4, %6;\n\t"
-        "addc.u64 %2, 0, 0;"
-        : "=&l"(lo), "=&l"(hi), "=&l"(c)
-        : "l"(a.lo), "l"(a.hi), "l"(b.lo), "l"(b.hi));
-    // subtract M when the sum overflowed 2^128 or is >= M  (M.hi is all ones)
-    bool ge = c || (hi == EZK_MOD_HI && lo >= EZK_MOD_LO);
-    if (ge) {
-        // s - M = s + (2^128 - M) - 2^128 = s + (45*2^40 - 1), dropping the carry
-        const uint64_t k = (45ULL << 40) - 1;
-        asm("add.cc.u64 %0, %0, %2;\n\t"
-            "addc.u64 %1, %1, 0;"
-            : "+l"(lo), "+l"(hi)
-            : "l"(k));
-    }
-    return fe_make(lo, hi);
+    fe s;
+    uint32_t c;
+    asm("add.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, %11;\n\t"
+        "addc.cc.u32 %3, %8, %12;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "=&r"(s.a0), "=&r"(s.a1), "=&r"(s.a2), "=&r"(s.a3), "=&r"(c)
+        : "r"(a.a0), "r"(a.a1), "r"(a.a2), "r"(a.a3), "r"(b.a0), "r"(b.a1), "r"(b.a2), "r"(b.a3));
+    // carry out of 2^128: s - M = s + K - 2^128 (branch-free; about half of all additions take it)
+    const uint32_t m0 = 0u - c, m1 = m0 & EZK_K1;
+    asm("add.cc.u32 %0, %0, %4;\n\t"
+        "addc.cc.u32 %1, %1, %5;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.u32 %3, %3, 0;"
+        : "+r"(s.a0), "+r"(s.a1), "+r"(s.a2), "+r"(s.a3)
+        : "r"(m0), "r"(m1));
+    if (s.a3 == 0xFFFFFFFFu) s = fe_fix_rare(s, 0);  // only values >= 2^128 - 2^96 can still be >= M
+    return s;
 }
 
 // r = a - b (mod M)
 __device__ __forceinline__ fe fe_sub(fe a, fe b) {
-    uint64_t lo, hi, bw;
-    asm("sub.cc.u64 %0, %3, %5;\n\t"
-        "subc.cc.u64 %1, %4, %6;\n\t"
-        "subc.u64 %2, 0, 0;"
-        : "=&l"(lo), "=&l"(hi), "=&l"(bw)
-        : "l"(a.lo), "l"(a.hi), "l"(b.lo), "l"(b.hi));
-    if (bw) {
-        // + M = - (45*2^40 - 1) mod 2^128
-        const uint64_t k = (45ULL << 40) - 1;
-        asm("sub.cc.u64 %0, %0, %2;\n\t"
-            "subc.u64 %1, %1, 0;"
-            : "+l"(lo), "+l"(hi)
-            : "l"(k));
-    }
-    return fe_make(lo, hi);
+    fe s;
+    uint32_t m0;
+    asm("sub.cc.u32 %0, %5, %9;\n\t"
+        "subc.cc.u32 %1, %6, %10;\n\t"
+        "subc.cc.u32 %2, %7, %11;\n\t"
+        "subc.cc.u32 %3, %8, %12;\n\t"
+        "subc.u32 %4, 0, 0;"
+        : "=&r"(s.a0), "=&r"(s.a1), "=&r"(s.a2), "=&r"(s.a3), "=&r"(m0)
+        : "r"(a.a0), "r"(a.a1), "r"(a.a2), "r"(a.a3), "r"(b.a0), "r"(b.a1), "r"(b.a2), "r"(b.a3));
+    // borrow: + M = - K (mod 2^128)
+    const uint32_t m1 = m0 & EZK_K1;
+    asm("sub.cc.u32 %0, %0, %4;\n\t"
+        "subc.cc.u32 %1, %1, %5;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.u32 %3, %3, 0;"
+        : "+r"(s.a0), "+r"(s.a1), "+r"(s.a2), "+r"(s.a3)
+        : "r"(m0), "r"(m1));
+    return s;
 }
 
 __device__ __forceinline__ fe fe_neg(fe a) { return fe_sub(fe_zero(), a); }
 
-// reduce a 256-bit value (r3:r2:r1:r0, 64-bit words) modulo M
-__device__ __forceinline__ fe fe_reduce256(uint64_t r0, uint64_t r1, uint64_t r2, uint64_t r3) {
-    // hi * 45 -> t2:t1:t0 (134 bits)
-    uint64_t t0 = r2 * 45ULL;
-    uint64_t t1 = __umul64hi(r2, 45ULL);
-    uint64_t t2;
-    {
-        uint64_t m_lo = r3 * 45ULL, m_hi = __umul64hi(r3, 45ULL);
-        asm("add.cc.u64 %0, %0, %2;\n\t"
-            "addc.u64 %1, %3, 0;"
-            : "+l"(t1), "=&l"(t2)
-            : "l"(m_lo), "l"(m_hi));
-    }
-    // u = t << 40 (174 bits)
-    uint64_t u0 = t0 << 40;
-    uint64_t u1 = (t1 << 40) | (t0 >> 24);
-    uint64_t u2 = (t2 << 40) | (t1 >> 24);
-    // v = u - hi  (>= 0)
-    asm("sub.cc.u64 %0, %0, %3;\n\t"
-        "subc.cc.u64 %1, %1, %4;\n\t"
-        "subc.u64 %2, %2, 0;"
-        : "+l"(u0), "+l"(u1), "+l"(u2)
-        : "l"(r2), "l"(r3));
-    // s = lo + v  -> top:s1:s0, top < 2^47
-    uint64_t s0, s1, top;
-    asm("add.cc.u64 %0, %3, %5;\n\t"
-        "addc.cc.u64 %1, %4, %6;\n\t"
-        "addc.u64 %2, %7, 0;"
-        : "=&l"(s0), "=&l"(s1), "=&l"(top)
-        : "l"(r0), "l"(r1), "l"(u0), "l"(u1), "l"(u2));
-    // second fold: top * (45*2^40 - 1) = (top*45 << 40) - top, < 2^93
-    uint64_t w = top * 45ULL;  // < 2^53
-    uint64_t w0 = w << 40, w1 = w >> 24;
-    asm("sub.cc.u64 %0, %0, %2;\n\t"
-        "subc.u64 %1, %1, 0;"
-        : "+l"(w0), "+l"(w1)
-        : "l"(top));
-    uint64_t c;
-    asm("add.cc.u64 %0, %0, %3;\n\t"
-        "addc.cc.u64 %1, %1, %4;\n\t"
-        "addc.u64 %2, 0, 0;"
-        : "+l"(s0), "+l"(s1), "=&l"(c)
-        : "l"(w0), "l"(w1));
-    const uint64_t k = (45ULL << 40) - 1;
-    if (c) {  // wrapped past 2^128 once more: add 2^128 mod M (cannot wrap again: s < 2^93 here)
-        asm("add.cc.u64 %0, %0, %2;\n\t"
-            "addc.u64 %1, %1, 0;"
-            : "+l"(s0), "+l"(s1)
-            : "l"(k));
-    }
-    if (s1 == EZK_MOD_HI && s0 >= EZK_MOD_LO) {  // final canonicalisation
-        asm("add.cc.u64 %0, %0, %2;\n\t"
-            "addc.u64 %1, %1, 0;"
-            : "+l"(s0), "+l"(s1)
-            : "l"(k));
-    }
-    return fe_make(s0, s1);
+// s (128 bits) + top * 2^128 (top = p1:p0 < 2^46)  ->  canonical element
+__device__ __forceinline__ fe fe_fold_top(fe s, uint32_t p0, uint32_t p1) {
+    uint32_t ov;
+    asm("{\n\t"
+        ".reg .u32 v1, v2, q0, q1, q2;\n\t"
+        "mul.lo.u32 v1, %5, 11520;\n\t"
+        "mul.hi.u32 v2, %5, 11520;\n\t"
+        "mad.lo.u32 v2, %6, 11520, v2;\n\t"  // top*11520 < 2^60
+        "sub.cc.u32 q0, 0, %5;\n\t"          // q = (top*11520 << 32) - top  (>= 0)
+        "subc.cc.u32 q1, v1, %6;\n\t"
+        "subc.u32 q2, v2, 0;\n\t"
+        "add.cc.u32 %0, %0, q0;\n\t"
+        "addc.cc.u32 %1, %1, q1;\n\t"
+        "addc.cc.u32 %2, %2, q2;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, 0, 0;\n\t"
+        "}"
+        : "+r"(s.a0), "+r"(s.a1), "+r"(s.a2), "+r"(s.a3), "=r"(ov)
+        : "r"(p0), "r"(p1));
+    if (ov | (uint32_t)(s.a3 == 0xFFFFFFFFu)) s = fe_fix_rare(s, ov);
+    return s;
+}
+
+// r[0..8) = a * b: even/odd column accumulation, 16 IMAD.WIDE.U32 with carry
+__device__ __forceinline__ void fe_mul256(const fe& a, const fe& b, uint32_t (&r)[8]) {
+    asm("{\n\t"
+        ".reg .u32 e0, e1, e2, e3, e4, e5, e6, e7, o0, o1, o2, o3, o4, o5, o6;\n\t"
+        // b0: even <- a0, a2 ; odd <- a1, a3
+        "mul.lo.u32 e0, %8, %12;\n\t"
+        "mul.hi.u32 e1, %8, %12;\n\t"
+        "mul.lo.u32 e2, %10, %12;\n\t"
+        "mul.hi.u32 e3, %10, %12;\n\t"
+        "mul.lo.u32 o0, %9, %12;\n\t"
+        "mul.hi.u32 o1, %9, %12;\n\t"
+        "mul.lo.u32 o2, %11, %12;\n\t"
+        "mul.hi.u32 o3, %11, %12;\n\t"
+        // b1: odd += a0, a2 ; even += a1, a3
+        "mad.lo.cc.u32 o0, %8, %13, o0;\n\t"
+        "madc.hi.cc.u32 o1, %8, %13, o1;\n\t"
+        "madc.lo.cc.u32 o2, %10, %13, o2;\n\t"
+        "madc.hi.cc.u32 o3, %10, %13, o3;\n\t"
+        "addc.u32 o4, 0, 0;\n\t"
+        "mad.lo.cc.u32 e2, %9, %13, e2;\n\t"
+        "madc.hi.cc.u32 e3, %9, %13, e3;\n\t"
+        "madc.lo.cc.u32 e4, %11, %13, 0;\n\t"
+        "madc.hi.u32 e5, %11, %13, 0;\n\t"
+        // b2: even += a0, a2 ; odd += a1, a3
+        "mad.lo.cc.u32 e2, %8, %14, e2;\n\t"
+        "madc.hi.cc.u32 e3, %8, %14, e3;\n\t"
+        "madc.lo.cc.u32 e4, %10, %14, e4;\n\t"
+        "madc.hi.cc.u32 e5, %10, %14, e5;\n\t"
+        "addc.u32 e6, 0, 0;\n\t"
+        "mad.lo.cc.u32 o2, %9, %14, o2;\n\t"
+        "madc.hi.cc.u32 o3, %9, %14, o3;\n\t"
+        "madc.lo.cc.u32 o4, %11, %14, o4;\n\t"
+        "madc.hi.u32 o5, %11, %14, 0;\n\t"
+        // b3: odd += a0, a2 ; even += a1, a3
+        "mad.lo.cc.u32 o2, %8, %15, o2;\n\t"
+        "madc.hi.cc.u32 o3, %8, %15, o3;\n\t"
+        "madc.lo.cc.u32 o4, %10, %15, o4;\n\t"
+        "madc.hi.cc.u32 o5, %10, %15, o5;\n\t"
+        "addc.u32 o6, 0, 0;\n\t"
+        "mad.lo.cc.u32 e4, %9, %15, e4;\n\t"
+        "madc.hi.cc.u32 e5, %9, %15, e5;\n\t"
+        "madc.lo.cc.u32 e6, %11, %15, e6;\n\t"
+        "madc.hi.u32 e7, %11, %15, 0;\n\t"
+        // r = even + (odd << 32)
+        "mov.u32 %0, e0;\n\t"
+        "add.cc.u32 %1, e1, o0;\n\t"
+        "addc.cc.u32 %2, e2, o1;\n\t"
+        "addc.cc.u32 %3, e3, o2;\n\t"
+        "addc.cc.u32 %4, e4, o3;\n\t"
+        "addc.cc.u32 %5, e5, o4;\n\t"
+        "addc.cc.u32 %6, e6, o5;\n\t"
+        "addc.u32 %7, e7, o6;\n\t"
+        "}"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(a.a0), "r"(a.a1), "r"(a.a2), "r"(a.a3), "r"(b.a0), "r"(b.a1), "r"(b.a2), "r"(b.a3));
+}
+
+// (r[0..8)) mod M, canonical.  lo + hi*2^128 = lo + (hi*11520 << 32) - hi.
+__device__ __forceinline__ fe fe_reduce256(const uint32_t (&r)[8]) {
+    fe s;
+    uint32_t p0, p1;
+    asm("{\n\t"
+        ".reg .u32 x1, x2, x3, x4, y2, y3, y4, y5;\n\t"
+        // X = (h0*11520 + l2:l1) , (h2*11520 + l3) chained ; Y = h1*11520, h3*11520
+        "mad.lo.cc.u32 x1, %10, 11520, %7;\n\t"
+        "madc.hi.cc.u32 x2, %10, 11520, %8;\n\t"
+        "madc.lo.cc.u32 x3, %12, 11520, %9;\n\t"
+        "madc.hi.u32 x4, %12, 11520, 0;\n\t"
+        "mul.lo.u32 y2, %11, 11520;\n\t"
+        "mul.hi.u32 y3, %11, 11520;\n\t"
+        "mul.lo.u32 y4, %13, 11520;\n\t"
+        "mul.hi.u32 y5, %13, 11520;\n\t"
+        "add.cc.u32 x2, x2, y2;\n\t"
+        "addc.cc.u32 x3, x3, y3;\n\t"
+        "addc.cc.u32 x4, x4, y4;\n\t"
+        "addc.u32 y5, y5, 0;\n\t"
+        // S = (l0, x1, x2, x3 | x4, y5) - h   (>= 0)
+        "sub.cc.u32 %0, %6, %10;\n\t"
+        "subc.cc.u32 %1, x1, %11;\n\t"
+        "subc.cc.u32 %2, x2, %12;\n\t"
+        "subc.cc.u32 %3, x3, %13;\n\t"
+        "subc.cc.u32 %4, x4, 0;\n\t"
+        "subc.u32 %5, y5, 0;\n\t"
+        "}"
+        : "=&r"(s.a0), "=&r"(s.a1), "=&r"(s.a2), "=&r"(s.a3), "=&r"(p0), "=&r"(p1)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+    return fe_fold_top(s, p0, p1);
 }
 
 __device__ __forceinline__ fe fe_mul(fe a, fe b) {
-    // 256-bit schoolbook product on 64-bit limbs (lowered by ptxas to IMAD.WIDE chains)
-    uint64_t p0l = a.lo * b.lo, p0h = __umul64hi(a.lo, b.lo);
-    uint64_t p1l = a.lo * b.hi, p1h = __umul64hi(a.lo, b.hi);
-    uint64_t p2l = a.hi * b.lo, p2h = __umul64hi(a.hi, b.lo);
-    uint64_t p3l = a.hi * b.hi, p3h = __umul64hi(a.hi, b.hi);
-    uint64_t r0 = p0l, r1, r2, r3;
-    asm("add.cc.u64 %0, %3, %4;\n\t"
-        "addc.cc.u64 %1, %5, %6;\n\t"
-        "addc.u64 %2, %7, 0;\n\t"
-        "add.cc.u64 %0, %0, %8;\n\t"
-        "addc.cc.u64 %1, %1, %9;\n\t"
-        "addc.u64 %2, %2, 0;"
-        : "=&l"(r1), "=&l"(r2), "=&l"(r3)
-        : "l"(p0h), "l"(p1l), "l"(p1h), "l"(p3l), "l"(p3h), "l"(p2l), "l"(p2h));
-    return fe_reduce256(r0, r1, r2, r3);
+    uint32_t r[8];
+    fe_mul256(a, b, r);
+    return fe_reduce256(r);
 }
 
 __device__ __forceinline__ fe fe_sqr(fe a) { return fe_mul(a, a); }
 
-// a * small (small < 2^32), cheaper than a full product
-__device__ __forceinline__ fe fe_mul_small(fe a, uint32_t s) {
-    uint64_t r0 = a.lo * s, c0 = __umul64hi(a.lo, (uint64_t)s);
-    uint64_t r1 = a.hi * s, r2 = __umul64hi(a.hi, (uint64_t)s);
-    asm("add.cc.u64 %0, %0, %2;\n\t"
-        "addc.u64 %1, %1, 0;"
-        : "+l"(r1), "+l"(r2)
-        : "l"(c0));
-    return fe_reduce256(r0, r1, r2, 0);
+// a * small (small < 2^32): 4 IMAD.WIDE + the small fold
+__device__ __forceinline__ fe fe_mul_small(fe a, uint32_t k) {
+    fe s;
+    uint32_t p0;
+    asm("{\n\t"
+        ".reg .u32 t1, t3;\n\t"
+        "mul.lo.u32 %0, %5, %9;\n\t"
+        "mul.hi.u32 %1, %5, %9;\n\t"
+        "mul.lo.u32 %2, %7, %9;\n\t"
+        "mul.hi.u32 %3, %7, %9;\n\t"
+        "mul.lo.u32 t1, %6, %9;\n\t"
+        "mul.hi.u32 %4, %8, %9;\n\t"
+        "mul.lo.u32 t3, %8, %9;\n\t"
+        "add.cc.u32 %1, %1, t1;\n\t"
+        "madc.hi.cc.u32 %2, %6, %9, %2;\n\t"
+        "addc.cc.u32 %3, %3, t3;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "}"
+        : "=&r"(s.a0), "=&r"(s.a1), "=&r"(s.a2), "=&r"(s.a3), "=&r"(p0)
+        : "r"(a.a0), "r"(a.a1), "r"(a.a2), "r"(a.a3), "r"(k));
+    return fe_fold_top(s, p0, 0);
 }
 
 __device__ __forceinline__ fe fe_pow(fe b, uint64_t e) {
