@@ -3,12 +3,16 @@
 // Decomposition (mixed-radix, natural order in and out, no bit-reversal pass over HBM):
 //   n = n_1 * n_2 (* n_3);  input index m = m_1 + n_1 m_2 + n_1 n_2 m_3.
 //   pass i (i = p..2, "strided"): size-n_i transform over m_i at stride n_1..n_{i-1}, in place, followed by
-//       the twiddle w_{N_i}^{lo * j_i}, N_i = n_1..n_i, lo = index below digit i.  A CTA stages n_i x 8
-//       elements (8 adjacent lo values = 128-byte segments) in shared memory.
+//       the twiddle w_{N_i}^{lo * j_i}, N_i = n_1..n_i, lo = index below digit i.  A CTA handles n_i x lanes
+//       elements (lanes = 8 or 4 adjacent lo values = 128/64-byte global segments).
 //   pass 1 ("final"): size-n_1 transform over contiguous runs, written out of place to the natural output
-//       index j = j_p + n_p (j_{p-1} + ... n_2 j_1); a CTA handles 8 runs whose outputs are adjacent
-//       (or the 8 LDE cosets of one run), so global writes are again 128-byte segments.
-// Inside a tile: radix-2 decimation-in-frequency stages on shared memory, output taken bit-reversed.
+//       index j = j_p + n_p (j_{p-1} + ... n_2 j_1); a CTA handles `lanes` runs whose outputs are adjacent
+//       (or LDE cosets of one run), so global writes are again 64..128-byte segments.
+// Inside a tile: radix-8 decimation-in-frequency steps on REGISTERS (each thread holds 8 elements = three
+// butterfly stages between shared-memory exchanges; a leading radix-2/4 step absorbs log2(n_i) mod 3); the
+// first step reads global memory straight into registers and the last one stores straight from registers, so a
+// 2^9-point tile crosses shared memory twice instead of nine times.  The integer pipe, not HBM, bounds these
+// kernels: ~0.5 modmul (58 instr) + 1 add/sub (~10 instr) per element per stage.
 #include "ntt.cuh"
 #include "../field/f128.cuh"
 #include "../field/f128_host.h"
@@ -21,84 +25,216 @@ using namespace dev;
 
 namespace {
 
-constexpr int kLanes = 8;        // adjacent elements handled together (8 x 16 B = one 128-byte line)
-constexpr int kPad = kLanes + 1; // shared-memory row pitch (elements) -> conflict-free transposed access
-constexpr int kThreads = 512;
+constexpr int kThreads = 256;
+constexpr uint32_t kTileElems = 4096;  // field elements staged per CTA (64 KiB): S points x lanes
 
-__device__ __forceinline__ uint32_t bitrev32(uint32_t x, uint32_t bits) { return __brev(x) >> (32 - bits); }
+// lanes (independent transforms handled side by side so that global segments are 64..128 bytes)
+__host__ __device__ __forceinline__ uint32_t lanes_log_for(uint32_t log_s) { return log_s <= 9 ? 3u : 2u; }
 
-// in-tile DIF transform over the row index of tile[row * pitch + lane]; rows = 2^log_s
-__device__ __forceinline__ void tile_dif(uint4* tile, uint32_t log_s, uint32_t lanes_log, uint32_t pitch,
-                                         const uint4* __restrict__ roots) {
-    const uint32_t half_total = (1u << (log_s - 1)) << lanes_log;
-    for (int lh = (int)log_s - 1; lh >= 0; lh--) {
-        const uint32_t h = 1u << lh;
-        for (uint32_t b = threadIdx.x; b < half_total; b += blockDim.x) {
-            uint32_t lane = b & ((1u << lanes_log) - 1), k = b >> lanes_log;
-            uint32_t off = k & (h - 1), blk = k >> lh;
-            uint32_t i0 = (blk << (lh + 1)) + off, i1 = i0 + h;
-            fe a = fe_load(tile + i0 * pitch + lane), c = fe_load(tile + i1 * pitch + lane);
-            fe sum = fe_add(a, c), dif = fe_sub(a, c);
-            if (off != 0) {
-                // w_S^(off * S / 2h): exponent is a multiple of 2^(28-log_s) -> single table load
-                fe w = fe_root_pow(roots, log_s, (uint64_t)off << (log_s - 1 - lh));
-                dif = fe_mul(dif, w);
-            }
-            fe_store(tile + i0 * pitch + lane, sum);
-            fe_store(tile + i1 * pitch + lane, dif);
+// w_8^1..3 for the in-register 8-point butterflies: [0] forward, [1] inverse
+__constant__ uint4 c_w8[2][4];
+
+// compact per-size twiddle tables: tw[(1 << k) + e] = w_{2^k}^e, e < 2^k, k <= kTwMaxLog
+constexpr uint32_t kTwMaxLog = 11;
+
+__device__ __forceinline__ fe tw_at(const uint4* __restrict__ tw, uint32_t log_size, uint32_t e) {
+    return fe_ldg(tw + (1u << log_size) + e);
+}
+
+__device__ __forceinline__ void bf(fe& a, fe& b) {
+    fe s = fe_add(a, b), d = fe_sub(a, b);
+    a = s, b = d;
+}
+__device__ __forceinline__ void bf_w(fe& a, fe& b, const fe& w) {
+    fe s = fe_add(a, b), d = fe_sub(a, b);
+    a = s, b = fe_mul(d, w);
+}
+__device__ __forceinline__ void swap_fe(fe& a, fe& b) {
+    fe t = a;
+    a = b, b = t;
+}
+
+// x[k] <- sum_p x[p] w_8^(pk): three decimation-in-frequency stages on registers, 5 constant multiplications
+__device__ __forceinline__ void dft8(fe (&x)[8], uint32_t inv) {
+    const fe w1 = fe_from(c_w8[inv][1]), w2 = fe_from(c_w8[inv][2]), w3 = fe_from(c_w8[inv][3]);
+    bf(x[0], x[4]);
+    bf_w(x[1], x[5], w1);
+    bf_w(x[2], x[6], w2);
+    bf_w(x[3], x[7], w3);
+    bf(x[0], x[2]);
+    bf_w(x[1], x[3], w2);
+    bf(x[4], x[6]);
+    bf_w(x[5], x[7], w2);
+    bf(x[0], x[1]);
+    bf(x[2], x[3]);
+    bf(x[4], x[5]);
+    bf(x[6], x[7]);
+    // register r now holds frequency bitrev3(r): put frequency k into x[k]
+    swap_fe(x[1], x[4]);
+    swap_fe(x[3], x[6]);
+}
+
+// 4-point DFT of (m0..m3): X_k = sum_j m_j w_4^(jk), returned in natural order in the same registers
+__device__ __forceinline__ void dft4(fe& m0, fe& m1, fe& m2, fe& m3, uint32_t inv) {
+    const fe w2 = fe_from(c_w8[inv][2]);  // w_4
+    bf(m0, m2);
+    bf_w(m1, m3, w2);
+    bf(m0, m1);
+    bf(m2, m3);
+    swap_fe(m1, m2);
+}
+
+// One radix-2^a step (a = 1, 2, 3) of a decimation-in-frequency transform of size 2^log_cur on the 8 registers a
+// thread holds: slot p (p = 0..7) is position q + p * 2^(log_cur-3) of the sub-transform.  On return x[p'] is the
+// value to put back into slot p' (in place), already multiplied by its twiddle w_{2^log_cur}^(q' m').
+__device__ __forceinline__ void radix_step(fe (&x)[8], uint32_t a, uint32_t log_cur, uint32_t q, uint32_t inv,
+                                           const uint4* __restrict__ tw) {
+    const uint32_t eighth = 1u << (log_cur - 3);
+    if (a == 3) {
+        dft8(x, inv);
+        if (log_cur > 3 && q != 0) {
+#pragma unroll
+            for (int k = 1; k < 8; k++) x[k] = fe_mul(x[k], tw_at(tw, log_cur, q * k));
         }
-        __syncthreads();
+    } else if (a == 2) {
+        // two 4-point butterflies: h = p & 1 selects q' = q + h * eighth, m = p >> 1 is the digit
+        dft4(x[0], x[2], x[4], x[6], inv);
+        dft4(x[1], x[3], x[5], x[7], inv);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t qq = q + h * eighth;
+            if (qq != 0) {
+#pragma unroll
+                for (int m = 1; m < 4; m++) x[2 * m + h] = fe_mul(x[2 * m + h], tw_at(tw, log_cur, qq * m));
+            }
+        }
+    } else {
+        // four 2-point butterflies: h = p & 3, digit m = p >> 2
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+            const uint32_t qq = q + h * eighth;
+            if (qq != 0) {
+                bf_w(x[h], x[h + 4], tw_at(tw, log_cur, qq));
+            } else {
+                bf(x[h], x[h + 4]);
+            }
+        }
     }
 }
 
+// digits of a position, most significant first: a1 bits, then 3-bit digits; returns the frequency index
+// (digits in reverse order, each digit's bits kept in order)
+__device__ __forceinline__ uint32_t digit_reverse(uint32_t i, uint32_t log_s, uint32_t a1) {
+    uint32_t j = 0, shift = 0, rem = log_s, a = a1;
+    while (rem) {
+        rem -= a;
+        j |= ((i >> rem) & ((1u << a) - 1)) << shift;
+        shift += a;
+        a = 3;
+    }
+    return j;
+}
+
+// Size-2^log_s transforms of `lanes` interleaved sequences by one CTA.  Every thread keeps 8 elements in
+// registers per step; steps exchange through shared memory (tile[i * lanes + lane], lanes fastest so that a
+// quarter-warp always touches 8 consecutive 16-byte words); the first step reads global memory through
+// P.load(lane, i) and the last writes through P.store(lane, j, v) with j the natural frequency index.
+template <class Pass>
+__device__ __forceinline__ void tile_transform(Pass& P, uint4* tile, uint32_t log_s, uint32_t lanes_log, uint32_t inv,
+                                               const uint4* __restrict__ tw) {
+    const uint32_t steps = (log_s + 2) / 3, a1 = log_s - 3 * (steps - 1);
+    const uint32_t groups = (1u << (log_s - 3)) << lanes_log;
+    const uint32_t lane_mask = (1u << lanes_log) - 1;
+    uint32_t log_cur = log_s;
+    for (uint32_t step = 0; step < steps; step++) {
+        const uint32_t a = step == 0 ? a1 : 3;
+        const bool first = step == 0, last = step + 1 == steps;
+        const uint32_t sh = log_cur - 3;
+        for (uint32_t u = threadIdx.x; u < groups; u += blockDim.x) {
+            const uint32_t lane = u & lane_mask, g = u >> lanes_log;
+            const uint32_t q = g & ((1u << sh) - 1);
+            const uint32_t i0 = ((g >> sh) << log_cur) | q;  // slot 0; slot p adds p << sh
+            fe x[8];
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                const uint32_t i = i0 + ((uint32_t)p << sh);
+                x[p] = first ? P.load(lane, i) : fe_load(tile + (i << lanes_log) + lane);
+            }
+            radix_step(x, a, log_cur, q, inv, tw);
+            if (last) {
+                // sh == 0: i = 8 g + p and the last digit is the most significant part of the frequency
+                const uint32_t jg = digit_reverse(i0, log_s, a1);
+#pragma unroll
+                for (int p = 0; p < 8; p++) P.store(lane, jg + ((uint32_t)p << (log_s - 3)), x[p]);
+            } else {
+#pragma unroll
+                for (int p = 0; p < 8; p++) fe_store(tile + ((i0 + ((uint32_t)p << sh)) << lanes_log) + lane, x[p]);
+            }
+        }
+        if (!last) __syncthreads();
+        log_cur -= a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pass i >= 2 ("strided"): size-n_i transform over digit i at stride n_1..n_{i-1}, in place, then the twiddle
+// w_{N_i}^(lo * j_i).  A tile is n_i points x `lanes` adjacent `lo` values.
 struct StridedArgs {
     const uint4* src;
     uint4* dst;
     uint64_t src_pitch, dst_pitch;  // per grid.y column, in elements
     uint32_t log_stride, log_s;     // stride = lo range, S = n_i
+    uint32_t lanes_log;
     uint32_t coset_first;           // LDE first pass: column y reads coefficient column y/8, scaled by w_L^(c*m), c = y%8
     uint32_t log_L;
-    const uint4* roots;
+    uint32_t inv;
+    const uint4* roots;             // two-level 2^28-th root table (forward or inverse)
+    const uint4* tw;                // compact per-size tables (same direction)
 };
 
-__global__ void __launch_bounds__(kThreads) ntt_strided_pass(StridedArgs a) {
-    extern __shared__ uint4 tile[];
-    const uint32_t S = 1u << a.log_s;
-    const uint64_t stride = 1ull << a.log_stride;
-    const uint32_t tiles_per_hi = (uint32_t)(stride / kLanes);
-    const uint32_t lo0 = (blockIdx.x % tiles_per_hi) * kLanes;
-    const uint64_t hi = blockIdx.x / tiles_per_hi;
-    const uint64_t base = lo0 + hi * (stride << a.log_s);
-    uint32_t col = blockIdx.y, coset = 0;
+struct StridedPass {
     const uint4* src;
-    if (a.coset_first) {
-        coset = col & 7;
-        src = a.src + (uint64_t)(col >> 3) * a.src_pitch;
-    } else {
-        src = a.src + (uint64_t)col * a.src_pitch;
-    }
-    uint4* dst = a.dst + (uint64_t)col * a.dst_pitch;
-    const uint32_t total = S * kLanes;
-    for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
-        uint32_t lane = e & (kLanes - 1), m = e >> 3;
-        uint64_t idx = base + lane + stride * m;
+    uint4* dst;
+    const uint4* roots;
+    uint64_t base;
+    uint32_t lo0, log_stride, log_N, coset, log_L;
+    __device__ __forceinline__ fe load(uint32_t lane, uint32_t m) const {
+        const uint64_t idx = base + lane + ((uint64_t)m << log_stride);
         fe v = fe_load(src + idx);
-        if (a.coset_first && coset != 0) v = fe_mul(v, fe_root_pow(a.roots, a.log_L, (uint64_t)coset * idx));
-        fe_store(tile + m * kLanes + lane, v);
+        if (coset != 0) v = fe_mul(v, fe_root_pow(roots, log_L, (uint64_t)coset * idx));
+        return v;
     }
-    __syncthreads();
-    tile_dif(tile, a.log_s, 3, kLanes, a.roots);
-    const uint32_t log_N = a.log_stride + a.log_s;
-    for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
-        uint32_t lane = e & (kLanes - 1), pos = e >> 3;
-        uint32_t j = bitrev32(pos, a.log_s);
-        fe v = fe_load(tile + pos * kLanes + lane);
-        uint64_t ex = (uint64_t)(lo0 + lane) * j;
-        if (ex != 0) v = fe_mul(v, fe_root_pow(a.roots, log_N, ex));
-        fe_store(dst + base + lane + stride * j, v);
+    __device__ __forceinline__ void store(uint32_t lane, uint32_t j, fe v) const {
+        const uint64_t ex = (uint64_t)(lo0 + lane) * j;
+        if (ex != 0) v = fe_mul(v, fe_root_pow(roots, log_N, ex));
+        fe_store(dst + base + lane + ((uint64_t)j << log_stride), v);
     }
+};
+
+__global__ void __launch_bounds__(kThreads, 3) ntt_strided_pass(StridedArgs a) {
+    extern __shared__ uint4 tile[];
+    const uint32_t lanes = 1u << a.lanes_log;
+    const uint32_t tiles_per_hi = (uint32_t)((1ull << a.log_stride) >> a.lanes_log);
+    StridedPass P;
+    P.lo0 = (blockIdx.x % tiles_per_hi) * lanes;
+    const uint64_t hi = blockIdx.x / tiles_per_hi;
+    P.base = P.lo0 + (hi << (a.log_stride + a.log_s));
+    const uint32_t col = blockIdx.y;
+    if (a.coset_first) {
+        P.coset = col & 7;
+        P.src = a.src + (uint64_t)(col >> 3) * a.src_pitch;
+    } else {
+        P.coset = 0;
+        P.src = a.src + (uint64_t)col * a.src_pitch;
+    }
+    P.dst = a.dst + (uint64_t)col * a.dst_pitch;
+    P.roots = a.roots;
+    P.log_stride = a.log_stride, P.log_N = a.log_stride + a.log_s, P.log_L = a.log_L;
+    tile_transform(P, tile, a.log_s, a.lanes_log, a.inv, a.tw);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// pass 1 ("final"): size-n_1 transform over contiguous runs, written out of place to the natural output index.
 struct FinalArgs {
     const uint4* src;
     uint4* dst;
@@ -106,93 +242,106 @@ struct FinalArgs {
     uint32_t log_n, log_s;          // S = n_1
     uint32_t passes;                // p in {1,2,3}
     uint32_t log_top;               // log2(n_p), the most significant storage digit (p >= 2)
-    uint32_t mode;                  // 0 plain, 1 LDE from tmp (8 cosets/tile), 2 LDE direct from coefficients (p = 1)
-    uint32_t lanes_log;             // 0 (one run per tile) or 3
+    uint32_t mode;                  // 0 plain, 1 LDE from tmp (lanes = cosets), 2 LDE direct from coefficients (p = 1)
+    uint32_t lanes_log;             // 0 (one run per tile), 2 or 3
     uint32_t log_L;
+    uint32_t inv;
     const uint4* roots;
+    const uint4* tw;
     const uint4* off_tab;
     NttScale scale;
 };
 
-__global__ void __launch_bounds__(kThreads) ntt_final_pass(FinalArgs a) {
-    extern __shared__ uint4 tile[];
-    const uint32_t S = 1u << a.log_s;
-    const uint32_t lanes = 1u << a.lanes_log;
-    const uint32_t pitch = lanes > 1 ? kPad : 1;
-    const uint32_t log_H = a.log_n - a.log_s;  // runs per column
-    const uint32_t col = blockIdx.y;
-    // which runs does this tile own?
-    uint64_t run0, run_step;  // run index of lane r = run0 + r * run_step
-    uint64_t out_base;        // output index (before the j_1 term) of lane 0
-    if (a.mode == 0) {
-        if (a.passes == 1) {
-            run0 = 0, run_step = 0, out_base = 0;
-        } else {
-            // hi' = rest + (H / n_p) * j_p ; tile owns j_p = jp0 .. jp0+7 for one `rest`
-            const uint32_t log_rest = log_H - a.log_top;
-            const uint32_t tiles_per_rest = (1u << a.log_top) / kLanes;
-            const uint64_t rest = blockIdx.x / tiles_per_rest;
-            const uint32_t jp0 = (blockIdx.x % tiles_per_rest) * kLanes;
-            run0 = rest + ((uint64_t)jp0 << log_rest);
-            run_step = 1ull << log_rest;
-            out_base = (rest << a.log_top) + jp0;  // j_p + n_p * rest
-        }
-    } else {
-        // LDE: one run (hi') per tile, the 8 lanes are the cosets
-        const uint64_t hp = blockIdx.x;
-        run0 = hp, run_step = 0;
-        if (a.passes <= 1) {
-            out_base = 0;
-        } else {
-            const uint32_t log_rest = log_H - a.log_top;
-            const uint64_t rest = hp & ((1ull << log_rest) - 1), jp = hp >> log_rest;
-            out_base = (rest << a.log_top) + jp;
-        }
+struct FinalPass {
+    const FinalArgs* a;
+    const uint4* src;   // column base (mode 0, 2) or coset-0 base of this column group (mode 1)
+    uint4* dst;
+    uint64_t run0, run_step, out_base;
+    uint32_t log_H, coset0;
+    __device__ __forceinline__ fe load(uint32_t lane, uint32_t m) const {
+        if (a->mode == 0) return fe_load(src + ((run0 + lane * run_step) << a->log_s) + m);
+        const uint32_t coset = coset0 + lane;
+        if (a->mode == 1) return fe_load(src + (uint64_t)coset * a->src_pitch + (run0 << a->log_s) + m);
+        fe v = fe_load(src + m);
+        if (coset != 0) v = fe_mul(v, fe_root_pow(a->roots, a->log_L, (uint64_t)coset * m));
+        return v;
     }
-    const uint32_t total = S << a.lanes_log;
-    // load: lanes are separate runs; consecutive threads read consecutive elements of one run
-    for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
-        uint32_t m = e & (S - 1), lane = e >> a.log_s;
-        fe v;
-        if (a.mode == 0) {
-            const uint4* src = a.src + (uint64_t)col * a.src_pitch;
-            v = fe_load(src + ((run0 + lane * run_step) << a.log_s) + m);
-        } else if (a.mode == 1) {
-            const uint4* src = a.src + ((uint64_t)col * 8 + lane) * a.src_pitch;
-            v = fe_load(src + (run0 << a.log_s) + m);
-        } else {
-            const uint4* src = a.src + (uint64_t)col * a.src_pitch;
-            v = fe_load(src + m);
-            if (lane != 0) v = fe_mul(v, fe_root_pow(a.roots, a.log_L, (uint64_t)lane * m));
-        }
-        fe_store(tile + m * pitch + lane, v);
-    }
-    __syncthreads();
-    tile_dif(tile, a.log_s, a.lanes_log, pitch, a.roots);
-    uint4* dst = a.dst + (uint64_t)col * a.dst_pitch;
-    for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
-        uint32_t lane = e & (lanes - 1), pos = e >> a.lanes_log;
-        uint32_t j1 = bitrev32(pos, a.log_s);
-        fe v = fe_load(tile + pos * pitch + lane);
+    __device__ __forceinline__ void store(uint32_t lane, uint32_t j1, fe v) const {
         uint64_t out;
-        if (a.mode == 0) {
+        if (a->mode == 0) {
             out = ((uint64_t)j1 << log_H) + out_base + lane;
-            if (a.scale.enabled) {
-                uint32_t ci = (uint32_t)(out >> a.scale.chunk_shift);
-                fe c = fe_make(a.scale.cvec[ci][0], a.scale.cvec[ci][1]);
-                if (a.scale.use_offset) c = fe_mul(c, fe_tab_pow(a.off_tab, (uint32_t)out));
+            if (a->scale.enabled) {
+                const uint32_t ci = (uint32_t)(out >> a->scale.chunk_shift);
+                fe c = fe_make(a->scale.cvec[ci][0], a->scale.cvec[ci][1]);
+                if (a->scale.use_offset) c = fe_mul(c, fe_tab_pow(a->off_tab, (uint32_t)out));
                 v = fe_mul(v, c);
             }
         } else {
-            out = ((((uint64_t)j1 << log_H) + out_base) << 3) + lane;
+            out = ((((uint64_t)j1 << log_H) + out_base) << 3) + coset0 + lane;
         }
         fe_store(dst + out, v);
     }
+};
+
+__global__ void __launch_bounds__(kThreads, 3) ntt_final_pass(const __grid_constant__ FinalArgs a) {
+    extern __shared__ uint4 tile[];
+    const uint32_t lanes = 1u << a.lanes_log;
+    const uint32_t col = blockIdx.y;
+    FinalPass P;
+    P.a = &a;
+    P.log_H = a.log_n - a.log_s;  // log2(runs per column)
+    P.coset0 = 0;
+    P.dst = a.dst + (uint64_t)col * a.dst_pitch;
+    if (a.mode == 0) {
+        P.src = a.src + (uint64_t)col * a.src_pitch;
+        if (a.passes == 1) {
+            P.run0 = 0, P.run_step = 0, P.out_base = 0;
+        } else {
+            // run index hi' = rest + (H / n_p) * j_p ; the tile owns j_p = jp0 .. jp0+lanes-1 for one `rest`
+            const uint32_t log_rest = P.log_H - a.log_top;
+            const uint32_t tiles_per_rest = (1u << a.log_top) >> a.lanes_log;
+            const uint64_t rest = blockIdx.x / tiles_per_rest;
+            const uint32_t jp0 = (blockIdx.x % tiles_per_rest) * lanes;
+            P.run0 = rest + ((uint64_t)jp0 << log_rest);
+            P.run_step = 1ull << log_rest;
+            P.out_base = (rest << a.log_top) + jp0;  // j_p + n_p * rest
+        }
+    } else {
+        // LDE: one run per tile, the lanes are cosets (all 8, or one half of them when lanes = 4)
+        const uint32_t halves_log = 3 - a.lanes_log;
+        const uint64_t hp = blockIdx.x >> halves_log;
+        P.coset0 = (blockIdx.x & ((1u << halves_log) - 1)) << a.lanes_log;
+        P.run0 = hp, P.run_step = 0;
+        P.src = a.mode == 1 ? a.src + (uint64_t)col * 8 * a.src_pitch : a.src + (uint64_t)col * a.src_pitch;
+        if (a.passes <= 1) {
+            P.out_base = 0;
+        } else {
+            const uint32_t log_rest = P.log_H - a.log_top;
+            const uint64_t rest = hp & ((1ull << log_rest) - 1), jp = hp >> log_rest;
+            P.out_base = (rest << a.log_top) + jp;
+        }
+    }
+    tile_transform(P, tile, a.log_s, a.lanes_log, a.inv, a.tw);
 }
 
-size_t tile_bytes(uint32_t log_s, uint32_t lanes, bool padded) {
-    return ((size_t)1 << log_s) * (lanes > 1 ? (padded ? kPad : kLanes) : 1) * sizeof(uint4);
+// n = 2 or 4 (single run, fewer points than one 8-element register group): direct summation, one thread per output
+__global__ void ntt_tiny_kernel(const uint4* src, uint64_t src_pitch, uint4* dst, uint64_t dst_pitch, uint32_t log_n,
+                                const uint4* roots, const uint4* off_tab, NttScale scale) {
+    const uint32_t n = 1u << log_n, j = threadIdx.x, col = blockIdx.x;
+    if (j >= n) return;
+    const uint4* x = src + (uint64_t)col * src_pitch;
+    fe acc = fe_zero();
+    for (uint32_t m = 0; m < n; m++) acc = fe_add(acc, fe_mul(fe_load(x + m), fe_root_pow(roots, log_n, (uint64_t)m * j)));
+    if (scale.enabled) {
+        const uint32_t ci = (uint32_t)((uint64_t)j >> scale.chunk_shift);
+        fe c = fe_make(scale.cvec[ci][0], scale.cvec[ci][1]);
+        if (scale.use_offset) c = fe_mul(c, fe_tab_pow(off_tab, j));
+        acc = fe_mul(acc, c);
+    }
+    fe_store(dst + (uint64_t)col * dst_pitch + j, acc);
 }
+
+size_t tile_bytes(uint32_t log_s, uint32_t lanes_log) { return (((size_t)1 << log_s) << lanes_log) * sizeof(uint4); }
 
 struct Plan {
     uint32_t passes;
@@ -218,17 +367,16 @@ Plan make_plan(uint32_t log_n, int max_tile_log) {
 bool g_attr_set = false;
 void ensure_smem_attr() {
     if (g_attr_set) return;
-    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileElems * 16)));
+    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileElems * 16)));
     g_attr_set = true;
 }
 
 // strided passes p..2 over `ncols` arrays of n elements: the first pass reads `first_src` and writes `buf`,
 // later passes run in place in `buf`.  With `coset` the first pass reads coefficient column y/8 and applies the
 // coset factor w_L^(c*m), c = y%8 (LDE).
-int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log_n, const uint4* roots,
-                const uint4* first_src, uint64_t first_src_pitch, bool coset, uint4* buf, uint64_t buf_pitch,
-                uint32_t ncols, uint32_t log_L) {
+int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log_n, bool inverse, const uint4* first_src,
+                uint64_t first_src_pitch, bool coset, uint4* buf, uint64_t buf_pitch, uint32_t ncols, uint32_t log_L) {
     int launches = 0;
     uint32_t log_stride = log_n;
     for (int i = (int)pl.passes - 1; i >= 1; i--) {
@@ -239,28 +387,37 @@ int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log
         a.src_pitch = first ? first_src_pitch : buf_pitch;
         a.dst = buf, a.dst_pitch = buf_pitch;
         a.log_stride = log_stride, a.log_s = pl.log_d[i];
+        a.lanes_log = lanes_log_for(a.log_s);
+        if (a.lanes_log > log_stride) a.lanes_log = log_stride;
         a.coset_first = (first && coset) ? 1 : 0;
         a.log_L = log_L;
-        a.roots = roots;
-        dim3 grid((unsigned)(((uint64_t)1 << (log_n - pl.log_d[i])) / kLanes), ncols);
+        a.inv = inverse ? 1 : 0;
+        a.roots = inverse ? t.root_inv : t.root_fwd;
+        a.tw = inverse ? t.tw_inv : t.tw_fwd;
+        dim3 grid((unsigned)(((uint64_t)1 << (log_n - pl.log_d[i])) >> a.lanes_log), ncols);
         {
             // compulsory traffic: every element of every column read once and written once (the 8 coset copies of
             // an LDE first pass share one read of the coefficient column)
             const uint64_t elems = (uint64_t)ncols << log_n;
             LaunchScope ls(s, K_NTT_STRIDED, (a.coset_first ? elems / 8 + elems : 2 * elems) * 16);
-            ntt_strided_pass<<<grid, kThreads, tile_bytes(pl.log_d[i], kLanes, false), s>>>(a);
+            ntt_strided_pass<<<grid, kThreads, tile_bytes(a.log_s, a.lanes_log), s>>>(a);
         }
         EZK_CUDA(cudaGetLastError());
         launches++;
     }
-    (void)t;
     return launches;
 }
 
 }  // namespace
 
 void ntt_tables_init(NttTables& t) {
-    auto build = [](Fp base) {
+    auto upload = [](const std::vector<Fp>& h) {
+        uint4* d = nullptr;
+        EZK_CUDA(cudaMalloc(&d, h.size() * sizeof(uint4)));
+        EZK_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+        return d;
+    };
+    auto build = [&](Fp base) {
         std::vector<Fp> h(2 * EZK_TAB_SIZE);
         Fp acc(1);
         for (uint32_t k = 0; k < EZK_TAB_SIZE; k++) {
@@ -273,25 +430,43 @@ void ntt_tables_init(NttTables& t) {
             h[EZK_TAB_SIZE + k] = acc;
             acc = acc * big;
         }
-        uint4* d = nullptr;
-        EZK_CUDA(cudaMalloc(&d, h.size() * sizeof(uint4)));
-        EZK_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-        return d;
+        return upload(h);
+    };
+    // compact per-size tables: entry (1 << k) + e = w_{2^k}^e
+    auto build_compact = [&](bool inv) {
+        std::vector<Fp> h((size_t)2 << kTwMaxLog);
+        for (uint32_t k = 0; k <= kTwMaxLog; k++) {
+            Fp w = root_of_unity(k);
+            if (inv) w = inverse(w);
+            Fp acc(1);
+            for (uint32_t e = 0; e < (1u << k); e++) {
+                h[(1u << k) + e] = acc;
+                acc = acc * w;
+            }
+        }
+        return h;
     };
     Fp w = root_of_unity(EZK_ROOT_LOG), o = Fp::from_u64(kDomainOffset);
     t.root_fwd = build(w);
     t.root_inv = build(inverse(w));
     t.off_fwd = build(o);
     t.off_inv = build(inverse(o));
+    std::vector<Fp> cf = build_compact(false), ci = build_compact(true);
+    t.tw_fwd = upload(cf);
+    t.tw_inv = upload(ci);
+    Fp w8[2][4];
+    for (int e = 0; e < 4; e++) w8[0][e] = cf[8 + e], w8[1][e] = ci[8 + e];
+    EZK_CUDA(cudaMemcpyToSymbol(c_w8, w8, sizeof(w8)));
     const char* env = getenv("EZK_NTT_TILE_LOG");
     if (env) {
         int v = atoi(env);
-        if (v >= 9 && v <= 10) t.max_tile_log = v;
+        if (v >= 6 && v <= 10) t.max_tile_log = v;
     }
 }
 
 void ntt_tables_free(NttTables& t) {
     cudaFree(t.root_fwd), cudaFree(t.root_inv), cudaFree(t.off_fwd), cudaFree(t.off_inv);
+    cudaFree(t.tw_fwd), cudaFree(t.tw_inv);
     t = NttTables{};
 }
 
@@ -299,12 +474,25 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
                 uint4* work, uint32_t ncols, uint32_t log_n, bool inverse, const NttScale* scale) {
     ensure_smem_attr();
     const uint4* roots = inverse ? t.root_inv : t.root_fwd;
+    NttScale sc{};
+    const uint4* off_tab = t.off_fwd;
+    if (scale) {
+        sc = *scale;
+        sc.enabled = 1;
+        off_tab = scale->use_offset == 2 ? t.off_inv : t.off_fwd;
+    }
+    if (log_n < 3) {
+        LaunchScope ls(s, K_NTT_FINAL, ((uint64_t)ncols << log_n) * 32);
+        ntt_tiny_kernel<<<ncols, 32, 0, s>>>(src, src_pitch, dst, dst_pitch, log_n, roots, off_tab, sc);
+        EZK_CUDA(cudaGetLastError());
+        return 1;
+    }
     Plan pl = make_plan(log_n, t.max_tile_log);
     const uint64_t n = 1ull << log_n;
     int launches = 0;
     FinalArgs a{};
     if (pl.passes >= 2) {
-        launches = run_strided(t, s, pl, log_n, roots, src, src_pitch, false, work, n, ncols, 0);
+        launches = run_strided(t, s, pl, log_n, inverse, src, src_pitch, false, work, n, ncols, 0);
         a.src = work, a.src_pitch = n;
     } else {
         a.src = src, a.src_pitch = src_pitch;
@@ -313,18 +501,18 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
     a.log_n = log_n, a.log_s = pl.log_d[0], a.passes = pl.passes;
     a.log_top = pl.passes >= 2 ? pl.log_d[pl.passes - 1] : 0;
     a.mode = 0;
-    a.lanes_log = pl.passes >= 2 ? 3 : 0;
+    a.lanes_log = pl.passes >= 2 ? lanes_log_for(a.log_s) : 0;
+    if (a.lanes_log > a.log_top) a.lanes_log = a.log_top;
+    a.inv = inverse ? 1 : 0;
     a.roots = roots;
-    if (scale) {
-        a.scale = *scale;
-        a.scale.enabled = 1;
-        a.off_tab = scale->use_offset == 2 ? t.off_inv : t.off_fwd;
-    }
+    a.tw = inverse ? t.tw_inv : t.tw_fwd;
+    a.off_tab = off_tab;
+    a.scale = sc;
     uint64_t runs = 1ull << (log_n - pl.log_d[0]);
-    dim3 grid((unsigned)(pl.passes >= 2 ? runs / kLanes : 1), ncols);
+    dim3 grid((unsigned)(pl.passes >= 2 ? runs >> a.lanes_log : 1), ncols);
     {
         LaunchScope ls(s, K_NTT_FINAL, ((uint64_t)ncols << log_n) * 32);
-        ntt_final_pass<<<grid, kThreads, tile_bytes(pl.log_d[0], 1u << a.lanes_log, true), s>>>(a);
+        ntt_final_pass<<<grid, kThreads, tile_bytes(a.log_s, a.lanes_log), s>>>(a);
     }
     EZK_CUDA(cudaGetLastError());
     return launches + 1;
@@ -333,7 +521,7 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
 int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t coeff_pitch, uint4* lde,
                 uint64_t lde_pitch, uint4* tmp, uint32_t ncols, uint32_t log_n) {
     ensure_smem_attr();
-    const uint4* roots = t.root_fwd;
+    if (log_n < 3) throw CudaError("lde_columns: n must be at least 8");
     Plan pl = make_plan(log_n, t.max_tile_log);
     const uint64_t n = 1ull << log_n;
     const uint32_t log_L = log_n + 3;
@@ -342,22 +530,25 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
     a.dst = lde, a.dst_pitch = lde_pitch;
     a.log_n = log_n, a.log_s = pl.log_d[0], a.passes = pl.passes;
     a.log_top = pl.passes >= 2 ? pl.log_d[pl.passes - 1] : 0;
-    a.lanes_log = 3;
+    a.lanes_log = lanes_log_for(a.log_s);
     a.log_L = log_L;
-    a.roots = roots;
+    a.inv = 0;
+    a.roots = t.root_fwd;
+    a.tw = t.tw_fwd;
+    a.off_tab = t.off_fwd;
     if (pl.passes == 1) {
         a.mode = 2;
         a.src = coeff, a.src_pitch = coeff_pitch;
     } else {
-        launches += run_strided(t, s, pl, log_n, roots, coeff, coeff_pitch, true, tmp, n, ncols * 8, log_L);
+        launches += run_strided(t, s, pl, log_n, false, coeff, coeff_pitch, true, tmp, n, ncols * 8, log_L);
         a.mode = 1;
         a.src = tmp, a.src_pitch = n;
     }
-    dim3 grid((unsigned)(1ull << (log_n - pl.log_d[0])), ncols);
+    dim3 grid((unsigned)((1ull << (log_n - pl.log_d[0])) << (3 - a.lanes_log)), ncols);
     {
         const uint64_t elems = (uint64_t)ncols << log_n;
         LaunchScope ls(s, K_NTT_FINAL, (pl.passes == 1 ? elems + 8 * elems : 16 * elems) * 16);
-        ntt_final_pass<<<grid, kThreads, tile_bytes(pl.log_d[0], 8, true), s>>>(a);
+        ntt_final_pass<<<grid, kThreads, tile_bytes(a.log_s, a.lanes_log), s>>>(a);
     }
     EZK_CUDA(cudaGetLastError());
     return launches + 1;

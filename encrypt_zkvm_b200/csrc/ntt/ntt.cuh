@@ -13,7 +13,10 @@ struct NttTables {
     uint4* root_inv = nullptr;  // powers of w^-1
     uint4* off_fwd = nullptr;   // powers of the domain offset o = 3
     uint4* off_inv = nullptr;   // powers of o^-1
-    int max_tile_log = 10;      // largest in-shared-memory transform (2^10 points x 8 lanes)
+    // compact per-size tables: entry (1 << k) + e = w_{2^k}^e (forward) / w_{2^k}^-e (inverse), k <= 11
+    uint4* tw_fwd = nullptr;
+    uint4* tw_inv = nullptr;
+    int max_tile_log = 10;      // largest single-CTA transform (2^10 points x 4 lanes, 2^9 x 8 lanes)
 };
 
 void ntt_tables_init(NttTables& t);
