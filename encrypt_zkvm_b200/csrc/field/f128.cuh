@@ -55,14 +55,14 @@ __device__ __forceinline__ void fe_add_k(fe& s) {
 }
 
 // Rarely taken tail of add / mul: `ov` = the value wrapped past 2^128 once; then canonicalise (s >= M -> s - M).
-static __device__ __noinline__ fe fe_fix_rare(fe s, uint32_t ov) {
+__device__ __forceinline__ fe fe_fix_rare(fe s, uint32_t ov) {
     if (ov) fe_add_k(s);
     if (s.a3 == 0xFFFFFFFFu && s.a2 == 0xFFFFFFFFu && (s.a1 > EZK_M1 || (s.a1 == EZK_M1 && s.a0 >= 1u))) fe_add_k(s);
     return s;
 }
 
-// r = a + b (mod M), canonical inputs -> canonical output
-__device__ __forceinline__ fe fe_add(fe a, fe b) {
+// a + b - [carry] * M: canonical unless the result lies in [M, 2^128), which needs limb 3 = all ones
+__device__ __forceinline__ fe fe_add_raw(fe a, fe b) {
     fe s;
     uint32_t c;
     asm("add.cc.u32 %0, %5, %9;\n\t"
@@ -80,7 +80,23 @@ __device__ __forceinline__ fe fe_add(fe a, fe b) {
         "addc.u32 %3, %3, 0;"
         : "+r"(s.a0), "+r"(s.a1), "+r"(s.a2), "+r"(s.a3)
         : "r"(m0), "r"(m1));
+    return s;
+}
+
+// r = a + b (mod M), canonical inputs -> canonical output
+__device__ __forceinline__ fe fe_add(fe a, fe b) {
+    fe s = fe_add_raw(a, b);
     if (s.a3 == 0xFFFFFFFFu) s = fe_fix_rare(s, 0);  // only values >= 2^128 - 2^96 can still be >= M
+    return s;
+}
+
+// Branch-free variants for straight-line butterfly code.  The rare tails (a sum in [M, 2^128); a product that
+// wrapped past 2^128 in the last fold or landed above 2^128 - 2^96) are NOT fixed here: `rare` becomes
+// 0xFFFFFFFF instead and the caller redoes the whole group with the exact functions.  Keeping the common path
+// free of branches lets ptxas interleave the independent carry chains of neighbouring butterflies.
+__device__ __forceinline__ fe fe_add_flag(fe a, fe b, uint32_t& rare) {
+    fe s = fe_add_raw(a, b);
+    rare = max(rare, s.a3);
     return s;
 }
 
@@ -108,9 +124,8 @@ __device__ __forceinline__ fe fe_sub(fe a, fe b) {
 
 __device__ __forceinline__ fe fe_neg(fe a) { return fe_sub(fe_zero(), a); }
 
-// s (128 bits) + top * 2^128 (top = p1:p0 < 2^46)  ->  canonical element
-__device__ __forceinline__ fe fe_fold_top(fe s, uint32_t p0, uint32_t p1) {
-    uint32_t ov;
+// s (128 bits) + top * 2^128 (top = p1:p0 < 2^46), modulo 2^128; ov = 1 when the sum wrapped (add K once more)
+__device__ __forceinline__ fe fe_fold_top_raw(fe s, uint32_t p0, uint32_t p1, uint32_t& ov) {
     asm("{\n\t"
         ".reg .u32 v1, v2, q0, q1, q2;\n\t"
         "mul.lo.u32 v1, %5, 11520;\n\t"
@@ -127,6 +142,13 @@ __device__ __forceinline__ fe fe_fold_top(fe s, uint32_t p0, uint32_t p1) {
         "}"
         : "+r"(s.a0), "+r"(s.a1), "+r"(s.a2), "+r"(s.a3), "=r"(ov)
         : "r"(p0), "r"(p1));
+    return s;
+}
+
+// ... -> canonical element
+__device__ __forceinline__ fe fe_fold_top(fe s, uint32_t p0, uint32_t p1) {
+    uint32_t ov;
+    s = fe_fold_top_raw(s, p0, p1, ov);
     if (ov | (uint32_t)(s.a3 == 0xFFFFFFFFu)) s = fe_fix_rare(s, ov);
     return s;
 }
@@ -188,10 +210,8 @@ __device__ __forceinline__ void fe_mul256(const fe& a, const fe& b, uint32_t (&r
         : "r"(a.a0), "r"(a.a1), "r"(a.a2), "r"(a.a3), "r"(b.a0), "r"(b.a1), "r"(b.a2), "r"(b.a3));
 }
 
-// (r[0..8)) mod M, canonical.  lo + hi*2^128 = lo + (hi*11520 << 32) - hi.
-__device__ __forceinline__ fe fe_reduce256(const uint32_t (&r)[8]) {
-    fe s;
-    uint32_t p0, p1;
+// first fold of a 256-bit value: lo + hi*2^128 = lo + (hi*11520 << 32) - hi = s + (p1:p0) * 2^128, p1:p0 < 2^46
+__device__ __forceinline__ void fe_reduce256_first(const uint32_t (&r)[8], fe& s, uint32_t& p0, uint32_t& p1) {
     asm("{\n\t"
         ".reg .u32 x1, x2, x3, x4, y2, y3, y4, y5;\n\t"
         // X = (h0*11520 + l2:l1) , (h2*11520 + l3) chained ; Y = h1*11520, h3*11520
@@ -217,6 +237,12 @@ __device__ __forceinline__ fe fe_reduce256(const uint32_t (&r)[8]) {
         "}"
         : "=&r"(s.a0), "=&r"(s.a1), "=&r"(s.a2), "=&r"(s.a3), "=&r"(p0), "=&r"(p1)
         : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+}
+
+__device__ __forceinline__ fe fe_reduce256(const uint32_t (&r)[8]) {
+    fe s;
+    uint32_t p0, p1;
+    fe_reduce256_first(r, s, p0, p1);
     return fe_fold_top(s, p0, p1);
 }
 
@@ -224,6 +250,17 @@ __device__ __forceinline__ fe fe_mul(fe a, fe b) {
     uint32_t r[8];
     fe_mul256(a, b, r);
     return fe_reduce256(r);
+}
+
+// branch-free product, see fe_add_flag
+__device__ __forceinline__ fe fe_mul_flag(fe a, fe b, uint32_t& rare) {
+    uint32_t r[8], p0, p1, ov;
+    fe s;
+    fe_mul256(a, b, r);
+    fe_reduce256_first(r, s, p0, p1);
+    s = fe_fold_top_raw(s, p0, p1, ov);
+    rare = max(rare, max(s.a3, 0u - ov));
+    return s;
 }
 
 __device__ __forceinline__ fe fe_sqr(fe a) { return fe_mul(a, a); }

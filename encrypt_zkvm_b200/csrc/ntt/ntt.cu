@@ -25,7 +25,6 @@ using namespace dev;
 
 namespace {
 
-constexpr int kThreads = 256;
 constexpr uint32_t kTileElems = 4096;  // field elements staged per CTA (64 KiB): S points x lanes
 
 // lanes (independent transforms handled side by side so that global segments are 64..128 bytes)
@@ -41,13 +40,40 @@ __device__ __forceinline__ fe tw_at(const uint4* __restrict__ tw, uint32_t log_s
     return fe_ldg(tw + (1u << log_size) + e);
 }
 
-__device__ __forceinline__ void bf(fe& a, fe& b) {
-    fe s = fe_add(a, b), d = fe_sub(a, b);
+// Arithmetic policy of a butterfly group.  FAST: branch-free operations that only record their rare tails in
+// `rare` (f128.cuh); the group is then recomputed with the exact policy, which happens a few times per proof.
+template <bool FAST>
+struct Arith {
+    uint32_t rare = 0;
+    __device__ __forceinline__ fe add(fe a, fe b) { return FAST ? fe_add_flag(a, b, rare) : fe_add(a, b); }
+    __device__ __forceinline__ fe sub(fe a, fe b) { return fe_sub(a, b); }
+    __device__ __forceinline__ fe mul(fe a, fe b) { return FAST ? fe_mul_flag(a, b, rare) : fe_mul(a, b); }
+    __device__ __forceinline__ bool tainted() const { return FAST && rare == 0xFFFFFFFFu; }
+};
+
+// b^e from a two-level table with the policy's product (see fe_tab_pow)
+template <class A>
+__device__ __forceinline__ fe tab_pow(A& ar, const uint4* __restrict__ tab, uint32_t e) {
+    const uint32_t lo = e & (EZK_TAB_SIZE - 1), hi = e >> EZK_TAB_BITS;
+    const fe a = fe_ldg(tab + lo), b = fe_ldg(tab + EZK_TAB_SIZE + hi);
+    if (hi == 0) return a;
+    if (lo == 0) return b;
+    return ar.mul(a, b);
+}
+template <class A>
+__device__ __forceinline__ fe root_pow(A& ar, const uint4* __restrict__ tab, uint32_t log_n, uint64_t e) {
+    return tab_pow(ar, tab, (uint32_t)(e & ((1ull << log_n) - 1)) << (EZK_ROOT_LOG - log_n));
+}
+
+template <class A>
+__device__ __forceinline__ void bf(A& ar, fe& a, fe& b) {
+    fe s = ar.add(a, b), d = ar.sub(a, b);
     a = s, b = d;
 }
-__device__ __forceinline__ void bf_w(fe& a, fe& b, const fe& w) {
-    fe s = fe_add(a, b), d = fe_sub(a, b);
-    a = s, b = fe_mul(d, w);
+template <class A>
+__device__ __forceinline__ void bf_w(A& ar, fe& a, fe& b, const fe& w) {
+    fe s = ar.add(a, b), d = ar.sub(a, b);
+    a = s, b = ar.mul(d, w);
 }
 __device__ __forceinline__ void swap_fe(fe& a, fe& b) {
     fe t = a;
@@ -55,70 +81,66 @@ __device__ __forceinline__ void swap_fe(fe& a, fe& b) {
 }
 
 // x[k] <- sum_p x[p] w_8^(pk): three decimation-in-frequency stages on registers, 5 constant multiplications
-__device__ __forceinline__ void dft8(fe (&x)[8], uint32_t inv) {
+template <class A>
+__device__ __forceinline__ void dft8(A& ar, fe (&x)[8], uint32_t inv) {
     const fe w1 = fe_from(c_w8[inv][1]), w2 = fe_from(c_w8[inv][2]), w3 = fe_from(c_w8[inv][3]);
-    bf(x[0], x[4]);
-    bf_w(x[1], x[5], w1);
-    bf_w(x[2], x[6], w2);
-    bf_w(x[3], x[7], w3);
-    bf(x[0], x[2]);
-    bf_w(x[1], x[3], w2);
-    bf(x[4], x[6]);
-    bf_w(x[5], x[7], w2);
-    bf(x[0], x[1]);
-    bf(x[2], x[3]);
-    bf(x[4], x[5]);
-    bf(x[6], x[7]);
+    bf(ar, x[0], x[4]);
+    bf_w(ar, x[1], x[5], w1);
+    bf_w(ar, x[2], x[6], w2);
+    bf_w(ar, x[3], x[7], w3);
+    bf(ar, x[0], x[2]);
+    bf_w(ar, x[1], x[3], w2);
+    bf(ar, x[4], x[6]);
+    bf_w(ar, x[5], x[7], w2);
+    bf(ar, x[0], x[1]);
+    bf(ar, x[2], x[3]);
+    bf(ar, x[4], x[5]);
+    bf(ar, x[6], x[7]);
     // register r now holds frequency bitrev3(r): put frequency k into x[k]
     swap_fe(x[1], x[4]);
     swap_fe(x[3], x[6]);
 }
 
 // 4-point DFT of (m0..m3): X_k = sum_j m_j w_4^(jk), returned in natural order in the same registers
-__device__ __forceinline__ void dft4(fe& m0, fe& m1, fe& m2, fe& m3, uint32_t inv) {
+template <class A>
+__device__ __forceinline__ void dft4(A& ar, fe& m0, fe& m1, fe& m2, fe& m3, uint32_t inv) {
     const fe w2 = fe_from(c_w8[inv][2]);  // w_4
-    bf(m0, m2);
-    bf_w(m1, m3, w2);
-    bf(m0, m1);
-    bf(m2, m3);
+    bf(ar, m0, m2);
+    bf_w(ar, m1, m3, w2);
+    bf(ar, m0, m1);
+    bf(ar, m2, m3);
     swap_fe(m1, m2);
 }
 
 // One radix-2^a step (a = 1, 2, 3) of a decimation-in-frequency transform of size 2^log_cur on the 8 registers a
 // thread holds: slot p (p = 0..7) is position q + p * 2^(log_cur-3) of the sub-transform.  On return x[p'] is the
 // value to put back into slot p' (in place), already multiplied by its twiddle w_{2^log_cur}^(q' m').
-__device__ __forceinline__ void radix_step(fe (&x)[8], uint32_t a, uint32_t log_cur, uint32_t q, uint32_t inv,
+template <class A>
+__device__ __forceinline__ void radix_step(A& ar, fe (&x)[8], uint32_t a, uint32_t log_cur, uint32_t q, uint32_t inv,
                                            const uint4* __restrict__ tw) {
     const uint32_t eighth = 1u << (log_cur - 3);
     if (a == 3) {
-        dft8(x, inv);
+        dft8(ar, x, inv);
         if (log_cur > 3 && q != 0) {
 #pragma unroll
-            for (int k = 1; k < 8; k++) x[k] = fe_mul(x[k], tw_at(tw, log_cur, q * k));
+            for (int k = 1; k < 8; k++) x[k] = ar.mul(x[k], tw_at(tw, log_cur, q * k));
         }
     } else if (a == 2) {
         // two 4-point butterflies: h = p & 1 selects q' = q + h * eighth, m = p >> 1 is the digit
-        dft4(x[0], x[2], x[4], x[6], inv);
-        dft4(x[1], x[3], x[5], x[7], inv);
+        dft4(ar, x[0], x[2], x[4], x[6], inv);
+        dft4(ar, x[1], x[3], x[5], x[7], inv);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint32_t qq = q + h * eighth;
             if (qq != 0) {
 #pragma unroll
-                for (int m = 1; m < 4; m++) x[2 * m + h] = fe_mul(x[2 * m + h], tw_at(tw, log_cur, qq * m));
+                for (int m = 1; m < 4; m++) x[2 * m + h] = ar.mul(x[2 * m + h], tw_at(tw, log_cur, qq * m));
             }
         }
     } else {
-        // four 2-point butterflies: h = p & 3, digit m = p >> 2
+        // four 2-point butterflies: h = p & 3, digit m = p >> 2 (w^0 = 1 for q' = 0)
 #pragma unroll
-        for (int h = 0; h < 4; h++) {
-            const uint32_t qq = q + h * eighth;
-            if (qq != 0) {
-                bf_w(x[h], x[h + 4], tw_at(tw, log_cur, qq));
-            } else {
-                bf(x[h], x[h + 4]);
-            }
-        }
+        for (int h = 0; h < 4; h++) bf_w(ar, x[h], x[h + 4], tw_at(tw, log_cur, q + h * eighth));
     }
 }
 
@@ -135,44 +157,86 @@ __device__ __forceinline__ uint32_t digit_reverse(uint32_t i, uint32_t log_s, ui
     return j;
 }
 
+struct StepCtx {
+    uint32_t log_s, lanes_log, inv, a, a1, log_cur, first, last;
+    const uint4* tw;
+};
+
+// One group of 8 elements of one step: gather (global memory through P.load on the first step, shared memory
+// otherwise), butterflies, and on the last step the pass's output factor (P.finish).  Returns true when a FAST
+// computation hit a rare tail and must be redone.
+template <bool FAST, class Pass>
+__device__ __forceinline__ bool group_compute(const Pass& P, const uint4* tile, const StepCtx& c, uint32_t lane, uint32_t i0,
+                                              uint32_t q, uint32_t jg, fe (&x)[8]) {
+    Arith<FAST> ar;
+    const uint32_t sh = c.log_cur - 3;
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const uint32_t i = i0 + ((uint32_t)p << sh);
+        x[p] = c.first ? P.load(ar, lane, i) : fe_load(tile + (i << c.lanes_log) + lane);
+    }
+    radix_step(ar, x, c.a, c.log_cur, q, c.inv, c.tw);
+    if (c.last) {
+#pragma unroll
+        for (int p = 0; p < 8; p++) x[p] = P.finish(ar, lane, jg + ((uint32_t)p << (c.log_s - 3)), x[p]);
+    }
+    return ar.tainted();
+}
+
+template <class Pass>
+__device__ __forceinline__ void group_store(const Pass& P, uint4* tile, const StepCtx& c, uint32_t lane, uint32_t i0,
+                                            uint32_t jg, const fe (&x)[8]) {
+    if (c.last) {
+#pragma unroll
+        for (int p = 0; p < 8; p++) P.store(lane, jg + ((uint32_t)p << (c.log_s - 3)), x[p]);
+    } else {
+        const uint32_t sh = c.log_cur - 3;
+#pragma unroll
+        for (int p = 0; p < 8; p++) fe_store(tile + ((i0 + ((uint32_t)p << sh)) << c.lanes_log) + lane, x[p]);
+    }
+}
+
+// the rare redo: exact arithmetic, computes and stores the group (kept out of line, off the hot path's registers)
+template <class Pass>
+__device__ __noinline__ void group_redo_exact(const Pass& P, uint4* tile, const StepCtx& c, uint32_t lane, uint32_t i0,
+                                              uint32_t q, uint32_t jg) {
+    fe x[8];
+    group_compute<false>(P, tile, c, lane, i0, q, jg, x);
+    group_store(P, tile, c, lane, i0, jg, x);
+}
+
 // Size-2^log_s transforms of `lanes` interleaved sequences by one CTA.  Every thread keeps 8 elements in
 // registers per step; steps exchange through shared memory (tile[i * lanes + lane], lanes fastest so that a
 // quarter-warp always touches 8 consecutive 16-byte words); the first step reads global memory through
 // P.load(lane, i) and the last writes through P.store(lane, j, v) with j the natural frequency index.
 template <class Pass>
-__device__ __forceinline__ void tile_transform(Pass& P, uint4* tile, uint32_t log_s, uint32_t lanes_log, uint32_t inv,
+__device__ __forceinline__ void tile_transform(const Pass& P, uint4* tile, uint32_t log_s, uint32_t lanes_log, uint32_t inv,
                                                const uint4* __restrict__ tw) {
-    const uint32_t steps = (log_s + 2) / 3, a1 = log_s - 3 * (steps - 1);
+    const uint32_t steps = (log_s + 2) / 3;
+    StepCtx c;
+    c.log_s = log_s, c.lanes_log = lanes_log, c.inv = inv, c.tw = tw;
+    c.a1 = log_s - 3 * (steps - 1);
+    c.log_cur = log_s;
     const uint32_t groups = (1u << (log_s - 3)) << lanes_log;
     const uint32_t lane_mask = (1u << lanes_log) - 1;
-    uint32_t log_cur = log_s;
     for (uint32_t step = 0; step < steps; step++) {
-        const uint32_t a = step == 0 ? a1 : 3;
-        const bool first = step == 0, last = step + 1 == steps;
-        const uint32_t sh = log_cur - 3;
+        c.a = step == 0 ? c.a1 : 3;
+        c.first = step == 0, c.last = step + 1 == steps;
+        const uint32_t sh = c.log_cur - 3;
         for (uint32_t u = threadIdx.x; u < groups; u += blockDim.x) {
             const uint32_t lane = u & lane_mask, g = u >> lanes_log;
             const uint32_t q = g & ((1u << sh) - 1);
-            const uint32_t i0 = ((g >> sh) << log_cur) | q;  // slot 0; slot p adds p << sh
+            const uint32_t i0 = ((g >> sh) << c.log_cur) | q;  // slot 0; slot p adds p << sh
+            // last step (sh == 0): i = 8 g + p and the last digit is the most significant part of the frequency
+            const uint32_t jg = c.last ? digit_reverse(i0, log_s, c.a1) : 0;
             fe x[8];
-#pragma unroll
-            for (int p = 0; p < 8; p++) {
-                const uint32_t i = i0 + ((uint32_t)p << sh);
-                x[p] = first ? P.load(lane, i) : fe_load(tile + (i << lanes_log) + lane);
-            }
-            radix_step(x, a, log_cur, q, inv, tw);
-            if (last) {
-                // sh == 0: i = 8 g + p and the last digit is the most significant part of the frequency
-                const uint32_t jg = digit_reverse(i0, log_s, a1);
-#pragma unroll
-                for (int p = 0; p < 8; p++) P.store(lane, jg + ((uint32_t)p << (log_s - 3)), x[p]);
-            } else {
-#pragma unroll
-                for (int p = 0; p < 8; p++) fe_store(tile + ((i0 + ((uint32_t)p << sh)) << lanes_log) + lane, x[p]);
-            }
+            if (group_compute<true>(P, tile, c, lane, i0, q, jg, x))
+                group_redo_exact(P, tile, c, lane, i0, q, jg);
+            else
+                group_store(P, tile, c, lane, i0, jg, x);
         }
-        if (!last) __syncthreads();
-        log_cur -= a;
+        if (!c.last) __syncthreads();
+        c.log_cur -= c.a;
     }
 }
 
@@ -198,20 +262,28 @@ struct StridedPass {
     const uint4* roots;
     uint64_t base;
     uint32_t lo0, log_stride, log_N, coset, log_L;
-    __device__ __forceinline__ fe load(uint32_t lane, uint32_t m) const {
-        const uint64_t idx = base + lane + ((uint64_t)m << log_stride);
-        fe v = fe_load(src + idx);
-        if (coset != 0) v = fe_mul(v, fe_root_pow(roots, log_L, (uint64_t)coset * idx));
+    // LDE first pass: the coset factor w_L^(c * idx), idx = lo + stride * m, splits into w_L^(c * stride * m)
+    // (applied on load: exponent with >= 14 trailing zero bits in the 2^28 table -> one load, no product) and
+    // w_L^(c * lo), constant along the transform, which is folded into the output twiddle's exponent:
+    // w_N^(lo j) w_L^(c lo) = w_L^(lo (8 j + c)).
+    template <class A>
+    __device__ __forceinline__ fe load(A& ar, uint32_t lane, uint32_t m) const {
+        fe v = fe_load(src + base + lane + ((uint64_t)m << log_stride));
+        if (coset != 0 && m != 0) v = ar.mul(v, root_pow(ar, roots, log_L, ((uint64_t)coset * m) << log_stride));
         return v;
     }
+    template <class A>
+    __device__ __forceinline__ fe finish(A& ar, uint32_t lane, uint32_t j, fe v) const {
+        const uint64_t ex = (uint64_t)(lo0 + lane) * (((uint64_t)j << (log_L - log_N)) + coset);
+        return ex != 0 ? ar.mul(v, root_pow(ar, roots, log_L, ex)) : v;
+    }
     __device__ __forceinline__ void store(uint32_t lane, uint32_t j, fe v) const {
-        const uint64_t ex = (uint64_t)(lo0 + lane) * j;
-        if (ex != 0) v = fe_mul(v, fe_root_pow(roots, log_N, ex));
         fe_store(dst + base + lane + ((uint64_t)j << log_stride), v);
     }
 };
 
-__global__ void __launch_bounds__(kThreads, 3) ntt_strided_pass(StridedArgs a) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) ntt_strided_pass(StridedArgs a) {
     extern __shared__ uint4 tile[];
     const uint32_t lanes = 1u << a.lanes_log;
     const uint32_t tiles_per_hi = (uint32_t)((1ull << a.log_stride) >> a.lanes_log);
@@ -229,7 +301,8 @@ __global__ void __launch_bounds__(kThreads, 3) ntt_strided_pass(StridedArgs a) {
     }
     P.dst = a.dst + (uint64_t)col * a.dst_pitch;
     P.roots = a.roots;
-    P.log_stride = a.log_stride, P.log_N = a.log_stride + a.log_s, P.log_L = a.log_L;
+    P.log_stride = a.log_stride, P.log_N = a.log_stride + a.log_s;
+    P.log_L = a.coset_first ? a.log_L : P.log_N;  // plain passes: exponent lo * j of w_N
     tile_transform(P, tile, a.log_s, a.lanes_log, a.inv, a.tw);
 }
 
@@ -258,32 +331,35 @@ struct FinalPass {
     uint4* dst;
     uint64_t run0, run_step, out_base;
     uint32_t log_H, coset0;
-    __device__ __forceinline__ fe load(uint32_t lane, uint32_t m) const {
+    template <class A>
+    __device__ __forceinline__ fe load(A& ar, uint32_t lane, uint32_t m) const {
         if (a->mode == 0) return fe_load(src + ((run0 + lane * run_step) << a->log_s) + m);
         const uint32_t coset = coset0 + lane;
         if (a->mode == 1) return fe_load(src + (uint64_t)coset * a->src_pitch + (run0 << a->log_s) + m);
         fe v = fe_load(src + m);
-        if (coset != 0) v = fe_mul(v, fe_root_pow(a->roots, a->log_L, (uint64_t)coset * m));
+        if (coset != 0) v = ar.mul(v, root_pow(ar, a->roots, a->log_L, (uint64_t)coset * m));
         return v;
     }
-    __device__ __forceinline__ void store(uint32_t lane, uint32_t j1, fe v) const {
-        uint64_t out;
-        if (a->mode == 0) {
-            out = ((uint64_t)j1 << log_H) + out_base + lane;
-            if (a->scale.enabled) {
-                const uint32_t ci = (uint32_t)(out >> a->scale.chunk_shift);
-                fe c = fe_make(a->scale.cvec[ci][0], a->scale.cvec[ci][1]);
-                if (a->scale.use_offset) c = fe_mul(c, fe_tab_pow(a->off_tab, (uint32_t)out));
-                v = fe_mul(v, c);
-            }
-        } else {
-            out = ((((uint64_t)j1 << log_H) + out_base) << 3) + coset0 + lane;
-        }
-        fe_store(dst + out, v);
+    __device__ __forceinline__ uint64_t out_index(uint32_t lane, uint32_t j1) const {
+        if (a->mode == 0) return ((uint64_t)j1 << log_H) + out_base + lane;
+        return ((((uint64_t)j1 << log_H) + out_base) << 3) + coset0 + lane;
     }
+    template <class A>
+    __device__ __forceinline__ fe finish(A& ar, uint32_t lane, uint32_t j1, fe v) const {
+        if (a->mode == 0 && a->scale.enabled) {
+            const uint64_t out = out_index(lane, j1);
+            const uint32_t ci = (uint32_t)(out >> a->scale.chunk_shift);
+            fe c = fe_make(a->scale.cvec[ci][0], a->scale.cvec[ci][1]);
+            if (a->scale.use_offset) c = ar.mul(c, tab_pow(ar, a->off_tab, (uint32_t)out));
+            v = ar.mul(v, c);
+        }
+        return v;
+    }
+    __device__ __forceinline__ void store(uint32_t lane, uint32_t j1, fe v) const { fe_store(dst + out_index(lane, j1), v); }
 };
 
-__global__ void __launch_bounds__(kThreads, 3) ntt_final_pass(const __grid_constant__ FinalArgs a) {
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) ntt_final_pass(const __grid_constant__ FinalArgs a) {
     extern __shared__ uint4 tile[];
     const uint32_t lanes = 1u << a.lanes_log;
     const uint32_t col = blockIdx.y;
@@ -364,12 +440,35 @@ Plan make_plan(uint32_t log_n, int max_tile_log) {
     return p;
 }
 
-bool g_attr_set = false;
+// launch shapes: 0 = 256 threads x 3 CTAs/SM (<= 85 registers), 1 = 512 threads x 2 CTAs/SM (<= 64 registers)
+int g_variant = -1;
 void ensure_smem_attr() {
-    if (g_attr_set) return;
-    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileElems * 16)));
-    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileElems * 16)));
-    g_attr_set = true;
+    if (g_variant >= 0) return;
+    const int bytes = (int)(kTileElems * 16);
+    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    const char* env = getenv("EZK_NTT_VARIANT");
+    g_variant = env ? atoi(env) : 0;
+}
+void launch_strided(dim3 grid, size_t smem, cudaStream_t s, const StridedArgs& a) {
+    if (g_variant == 1)
+        ntt_strided_pass<512, 2><<<grid, 512, smem, s>>>(a);
+    else if (g_variant == 2)
+        ntt_strided_pass<256, 2><<<grid, 256, smem, s>>>(a);
+    else
+        ntt_strided_pass<256, 3><<<grid, 256, smem, s>>>(a);
+}
+void launch_final(dim3 grid, size_t smem, cudaStream_t s, const FinalArgs& a) {
+    if (g_variant == 1)
+        ntt_final_pass<512, 2><<<grid, 512, smem, s>>>(a);
+    else if (g_variant == 2)
+        ntt_final_pass<256, 2><<<grid, 256, smem, s>>>(a);
+    else
+        ntt_final_pass<256, 3><<<grid, 256, smem, s>>>(a);
 }
 
 // strided passes p..2 over `ncols` arrays of n elements: the first pass reads `first_src` and writes `buf`,
@@ -400,7 +499,7 @@ int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log
             // an LDE first pass share one read of the coefficient column)
             const uint64_t elems = (uint64_t)ncols << log_n;
             LaunchScope ls(s, K_NTT_STRIDED, (a.coset_first ? elems / 8 + elems : 2 * elems) * 16);
-            ntt_strided_pass<<<grid, kThreads, tile_bytes(a.log_s, a.lanes_log), s>>>(a);
+            launch_strided(grid, tile_bytes(a.log_s, a.lanes_log), s, a);
         }
         EZK_CUDA(cudaGetLastError());
         launches++;
@@ -512,7 +611,7 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
     dim3 grid((unsigned)(pl.passes >= 2 ? runs >> a.lanes_log : 1), ncols);
     {
         LaunchScope ls(s, K_NTT_FINAL, ((uint64_t)ncols << log_n) * 32);
-        ntt_final_pass<<<grid, kThreads, tile_bytes(a.log_s, a.lanes_log), s>>>(a);
+        launch_final(grid, tile_bytes(a.log_s, a.lanes_log), s, a);
     }
     EZK_CUDA(cudaGetLastError());
     return launches + 1;
@@ -548,7 +647,7 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
     {
         const uint64_t elems = (uint64_t)ncols << log_n;
         LaunchScope ls(s, K_NTT_FINAL, (pl.passes == 1 ? elems + 8 * elems : 16 * elems) * 16);
-        ntt_final_pass<<<grid, kThreads, tile_bytes(a.log_s, a.lanes_log), s>>>(a);
+        launch_final(grid, tile_bytes(a.log_s, a.lanes_log), s, a);
     }
     EZK_CUDA(cudaGetLastError());
     return launches + 1;
