@@ -19,6 +19,16 @@ __device__ __forceinline__ fe domain_point(const uint4* __restrict__ roots, uint
     return fe_add(fe_add(w, w), w);
 }
 
+template <class A>
+__device__ __forceinline__ fe root_pow_policy(A& ar, const uint4* __restrict__ tab, uint32_t log_n, uint64_t e) {
+    const uint32_t ee = (uint32_t)(e & ((1ull << log_n) - 1)) << (EZK_ROOT_LOG - log_n);
+    const uint32_t lo = ee & (EZK_TAB_SIZE - 1), hi = ee >> EZK_TAB_BITS;
+    const fe a = fe_ldg(tab + lo), b = fe_ldg(tab + EZK_TAB_SIZE + hi);
+    if (hi == 0) return a;
+    if (lo == 0) return b;
+    return ar.mul(a, b);
+}
+
 __global__ void __launch_bounds__(128) pair_inverse_kernel(const uint4* __restrict__ roots, uint32_t log_L, fe a, fe b,
                                                            uint4* __restrict__ out) {
     const uint64_t L = 1ull << log_L;
@@ -61,16 +71,17 @@ struct LdeFrame {
 struct SumSink {
     const ConstraintParams* __restrict__ p;
     fe acc;
-    __device__ __forceinline__ void put(int j, fe v) { acc = fe_add(acc, fe_mul(ld2(p->tcoef[j]), v)); }
+    template <class A>
+    __device__ __forceinline__ void put(A& ar, int j, fe v) { acc = ar.add(acc, ar.mul(ld2(p->tcoef[j]), v)); }
 };
 
-__global__ void __launch_bounds__(128) constraint_kernel(const uint4* __restrict__ roots, const uint4* __restrict__ lde,
-                                                         uint64_t pitch, uint32_t log_L,
-                                                         const ConstraintParams* __restrict__ p,
-                                                         const uint4* __restrict__ inv_den, uint4* __restrict__ combined) {
+// combined evaluation of one LDE row; returns true when the FAST arithmetic hit a rare tail (value unusable)
+template <bool FAST>
+__device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, const uint4* __restrict__ lde, uint64_t pitch,
+                                               uint32_t log_L, const ConstraintParams* __restrict__ p,
+                                               const uint4* __restrict__ inv_den, uint64_t i, fe& result) {
     const uint64_t L = 1ull << log_L;
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L) return;
+    Arith<FAST> ar;
     LdeFrame f{lde, pitch, i, (i + 8) & (L - 1)};
     fe periodic[9];
     {
@@ -79,22 +90,47 @@ __global__ void __launch_bounds__(128) constraint_kernel(const uint4* __restrict
         for (int k = 0; k < 9; k++) periodic[k] = ld2(row[k]);
     }
     SumSink sink{p, fe_zero()};
-    eval_transition(f, periodic, reinterpret_cast<const AirConsts*>(p->inv_mds), p->delta, sink);
-    const fe x = domain_point(roots, log_L, i);
+    eval_transition(ar, f, periodic, reinterpret_cast<const AirConsts*>(p->inv_mds), p->delta, sink);
+    fe x = root_pow_policy(ar, roots, log_L, i);
+    x = ar.add(ar.add(x, x), x);  // x_i = 3 * w_L^i
     const fe a = ld2(p->g_last);
     // transition part: T * (x - g^(n-2)) (x - g^(n-1)) / (x^n - 1)
-    fe t = fe_mul(sink.acc, fe_mul(fe_sub(x, a), fe_sub(x, ld2(p->g_last2))));
-    t = fe_mul(t, ld2(p->inv_zn[i & 7]));
+    fe t = ar.mul(sink.acc, ar.mul(ar.sub(x, a), ar.sub(x, ld2(p->g_last2))));
+    t = ar.mul(t, ld2(p->inv_zn[i & 7]));
     // boundary groups: step 0 (12 assertions, all values zero) and step n-2 (10 assertions)
     fe s0 = fe_zero(), s1 = fe_zero();
 #pragma unroll
-    for (int k = 0; k < 12; k++) s0 = fe_add(s0, fe_mul(ld2(p->bcoef[k]), f.cur(p->bcol[k])));
+    for (int k = 0; k < 12; k++) s0 = ar.add(s0, ar.mul(ld2(p->bcoef[k]), f.cur(p->bcol[k])));
 #pragma unroll
-    for (int k = 12; k < 22; k++) s1 = fe_add(s1, fe_mul(ld2(p->bcoef[k]), fe_sub(f.cur(p->bcol[k]), ld2(p->bval[k]))));
+    for (int k = 12; k < 22; k++) s1 = ar.add(s1, ar.mul(ld2(p->bcoef[k]), ar.sub(f.cur(p->bcol[k]), ld2(p->bval[k]))));
     // B0/(x-1) + B1/(x-a) = (B0 (x-a) + B1 (x-1)) / ((x-1)(x-a))
-    fe num = fe_add(fe_mul(s0, fe_sub(x, a)), fe_mul(s1, fe_sub(x, fe_one())));
-    fe bsum = fe_mul(num, fe_ldg(inv_den + i));
-    fe_store(combined + i, fe_add(t, bsum));
+    const fe num = ar.add(ar.mul(s0, ar.sub(x, a)), ar.mul(s1, ar.sub(x, fe_one())));
+    const fe bsum = ar.mul(num, fe_ldg(inv_den + i));
+    result = ar.add(t, bsum);
+    return ar.tainted();
+}
+
+__device__ __noinline__ fe constraint_row_exact(const uint4* __restrict__ roots, const uint4* __restrict__ lde, uint64_t pitch,
+                                                uint32_t log_L, const ConstraintParams* __restrict__ p,
+                                                const uint4* __restrict__ inv_den, uint64_t i) {
+    fe r;
+    constraint_row<false>(roots, lde, pitch, log_L, p, inv_den, i, r);
+    return r;
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) constraint_kernel(const uint4* __restrict__ roots, const uint4* __restrict__ lde,
+                                                                   uint64_t pitch, uint32_t log_L,
+                                                                   const ConstraintParams* __restrict__ p,
+                                                                   const uint4* __restrict__ inv_den,
+                                                                   uint4* __restrict__ combined) {
+    const uint64_t L = 1ull << log_L;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    fe r;
+    if (constraint_row<true>(roots, lde, pitch, log_L, p, inv_den, i, r))
+        r = constraint_row_exact(roots, lde, pitch, log_L, p, inv_den, i);
+    fe_store(combined + i, r);
 }
 
 struct ArrayFrame {
@@ -105,7 +141,8 @@ struct ArrayFrame {
 };
 struct StoreSink {
     uint4* out;
-    __device__ __forceinline__ void put(int j, fe v) { fe_store(out + j, v); }
+    template <class A>
+    __device__ __forceinline__ void put(A&, int j, fe v) { fe_store(out + j, v); }
 };
 
 __global__ void frames_kernel(const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,
@@ -116,7 +153,8 @@ __global__ void frames_kernel(const uint4* cur, const uint4* nxt, const uint4* p
     fe per[9];
     for (int k = 0; k < 9; k++) per[k] = fe_load(periodic + 9 * t + k);
     StoreSink sink{out + 20 * t};
-    eval_transition(f, per, reinterpret_cast<const AirConsts*>(p->inv_mds), p->delta, sink);
+    Arith<false> ar;
+    eval_transition(ar, f, per, reinterpret_cast<const AirConsts*>(p->inv_mds), p->delta, sink);
 }
 
 }  // namespace
@@ -138,11 +176,21 @@ int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, uint32_t log_L, c
 int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde, uint64_t pitch, uint32_t log_L,
                          const ConstraintParams* params, const uint4* inv_den, uint4* combined) {
     const uint64_t L = 1ull << log_L;
-    const unsigned threads = 128;
+    static int variant = -1;
+    if (variant < 0) {
+        const char* env = getenv("EZK_CONSTRAINT_VARIANT");
+        variant = env ? atoi(env) : 0;
+    }
     {
         LaunchScope ls(s, K_CONSTRAINTS, L * 16 * (28 + 2));  // 28 columns + inv_den read, 1 column written
-        constraint_kernel<<<(unsigned)((L + threads - 1) / threads), threads, 0, s>>>(root_fwd, lde, pitch, log_L, params,
-                                                                                    inv_den, combined);
+        if (variant == 1)
+            constraint_kernel<128, 3><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, combined);
+        else if (variant == 2)
+            constraint_kernel<128, 6><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, combined);
+        else if (variant == 3)
+            constraint_kernel<128, 8><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, combined);
+        else
+            constraint_kernel<128, 4><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, combined);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

@@ -15,11 +15,11 @@ struct AirConsts {
     uint64_t inv_mds[16][2];  // crypto/src/rescue.rs:216-233 (full-size constants)
 };
 
-__device__ __forceinline__ fe fe_cube(fe x) { return fe_mul(fe_sqr(x), x); }
 
 // MDS * v with the reference's matrix (crypto/src/rescue.rs:197-214). Entries are small in absolute value
 // (positive p or M - q), so each product is a 128x32-bit multiply: r_i = sum_j sign_ij * |m_ij| * v_j.
-__device__ __forceinline__ void rescue_mds(const fe v[4], fe out[4]) {
+template <class A>
+__device__ __forceinline__ void rescue_mds(A& ar, const fe v[4], fe out[4]) {
     // row-major magnitudes and signs of MDS (negative entries are M - magnitude)
     const uint32_t mag[16] = {729, 1080, 390, 40, 29160, 42471, 14520, 1210, 882090, 1277640, 429429, 33880,
                               24698520, 35708310, 11935560, 925771};
@@ -30,63 +30,64 @@ __device__ __forceinline__ void rescue_mds(const fe v[4], fe out[4]) {
         fe acc = fe_zero();
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            fe t = fe_mul_small(v[j], mag[i * 4 + j]);
-            acc = neg[i * 4 + j] ? fe_sub(acc, t) : fe_add(acc, t);
+            fe t = ar.mul_small(v[j], mag[i * 4 + j]);
+            acc = neg[i * 4 + j] ? ar.sub(acc, t) : ar.add(acc, t);
         }
         out[i] = acc;
     }
 }
 
-__device__ __forceinline__ void rescue_inv_mds(const AirConsts* __restrict__ k, const fe v[4], fe out[4]) {
+template <class A>
+__device__ __forceinline__ void rescue_inv_mds(A& ar, const AirConsts* __restrict__ k, const fe v[4], fe out[4]) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         fe acc = fe_zero();
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             fe c = fe_make(k->inv_mds[i * 4 + j][0], k->inv_mds[i * 4 + j][1]);
-            acc = fe_add(acc, fe_mul(c, v[j]));
+            acc = ar.add(acc, ar.mul(c, v[j]));
         }
         out[i] = acc;
     }
 }
 
 // periodic: 9 values [hash_flag, ark0..ark7] for this row (air/src/lib.rs:201-205)
-template <class Frame, class Sink>
-__device__ __forceinline__ void eval_transition(const Frame& f, const fe* periodic, const AirConsts* __restrict__ k,
+template <class A, class Frame, class Sink>
+__device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe* periodic, const AirConsts* __restrict__ k,
                                                 uint32_t delta, Sink& sink) {
     const fe one = fe_one();
     // op bits: b0 = cur[5] (MSB) ... b4 = cur[1] (LSB)   (flags.rs:15-35)
     const fe b0 = f.cur(5), b1 = f.cur(4), b2 = f.cur(3), b3 = f.cur(2), b4 = f.cur(1);
-    const fe n0 = fe_sub(one, b0), n1 = fe_sub(one, b1), n2 = fe_sub(one, b2), n3 = fe_sub(one, b3), n4 = fe_sub(one, b4);
+    const fe n0 = ar.sub(one, b0), n1 = ar.sub(one, b1), n2 = ar.sub(one, b2), n3 = ar.sub(one, b3), n4 = ar.sub(one, b4);
     // shared sub-products of the degree-5 selectors (flags.rs:45-79); same field values as the reference's
     // left-to-right products because multiplication in the field is exact
-    const fe n3n4 = fe_mul(n3, n4), b3n4 = fe_mul(b3, n4), b3b4 = fe_mul(b3, b4), n3b4 = fe_mul(n3, b4);
-    const fe n0b1 = fe_mul(n0, b1);
-    const fe arith = fe_mul(n0b1, n2);                    // !b0 * b1 * !b2
-    const fe io = fe_mul(fe_mul(b0, n1), n2);             // b0 * !b1 * !b2
-    const fe f_add = fe_mul(arith, n3n4), f_sadd = fe_mul(arith, b3n4), f_add2 = fe_mul(arith, b3b4);
-    const fe f_mul = fe_mul(arith, n3b4), f_smul = fe_mul(fe_mul(n0b1, b2), n3n4);
-    const fe f_push = fe_mul(io, n3n4), f_read = fe_mul(io, n3b4), f_read2 = fe_mul(io, b3n4);
-    const fe f_noop = fe_mul(fe_mul(fe_mul(n0, n1), n2), n3n4);
+    const fe n3n4 = ar.mul(n3, n4), b3n4 = ar.mul(b3, n4), b3b4 = ar.mul(b3, b4), n3b4 = ar.mul(n3, b4);
+    const fe n0b1 = ar.mul(n0, b1);
+    const fe arith = ar.mul(n0b1, n2);                    // !b0 * b1 * !b2
+    const fe io = ar.mul(ar.mul(b0, n1), n2);             // b0 * !b1 * !b2
+    const fe f_add = ar.mul(arith, n3n4), f_sadd = ar.mul(arith, b3n4), f_add2 = ar.mul(arith, b3b4);
+    const fe f_mul = ar.mul(arith, n3b4), f_smul = ar.mul(ar.mul(n0b1, b2), n3n4);
+    const fe f_push = ar.mul(io, n3n4), f_read = ar.mul(io, n3b4), f_read2 = ar.mul(io, b3n4);
+    const fe f_noop = ar.mul(ar.mul(ar.mul(n0, n1), n2), n3n4);
 
     // r0: clk' - (clk + 1)                                   constrains.rs:95-97
-    sink.put(0, fe_sub(f.nxt(0), fe_add(f.cur(0), one)));
+    sink.put(ar, 0, ar.sub(f.nxt(0), ar.add(f.cur(0), one)));
     // r1: (d' - d - shr + shl) - 4*read2 + 4*add2            constrains.rs:103-106
     {
-        fe t = fe_sub(fe_sub(f.nxt(11), f.cur(11)), b0);
-        t = fe_add(t, b1);
-        t = fe_sub(t, fe_mul_small(f_read2, 4));
-        sink.put(1, fe_add(t, fe_mul_small(f_add2, 4)));
+        fe t = ar.sub(ar.sub(f.nxt(11), f.cur(11)), b0);
+        t = ar.add(t, b1);
+        t = ar.sub(t, ar.mul_small(f_read2, 4));
+        sink.put(ar, 1, ar.add(t, ar.mul_small(f_add2, 4)));
     }
     // r2: shr * shl                                          constrains.rs:99-101
-    sink.put(2, fe_mul(b0, b1));
+    sink.put(ar, 2, ar.mul(b0, b1));
 
     const fe s0 = f.cur(12), s1 = f.cur(13);
     const fe sn0 = f.nxt(12), sn1 = f.nxt(13);
     // r3: add * (s0' - (s0 + s1))                            constrains.rs:108-110
-    sink.put(3, fe_mul(f_add, fe_sub(sn0, fe_add(s0, s1))));
+    sink.put(ar, 3, ar.mul(f_add, ar.sub(sn0, ar.add(s0, s1))));
     // r6: mul * (s0' - s0*s1)                                constrains.rs:146-148
-    sink.put(6, fe_mul(f_mul, fe_sub(sn0, fe_mul(s0, s1))));
+    sink.put(ar, 6, ar.mul(f_mul, ar.sub(sn0, ar.mul(s0, s1))));
     // ciphertext ops: lwe_size = 5 (SURVEY 8b "constraints discovered")
     {
         fe acc_sadd = fe_zero(), acc_add2 = fe_zero(), acc_smul = fe_zero();
@@ -95,60 +96,60 @@ __device__ __forceinline__ void eval_transition(const Frame& f, const fe* period
             const fe snj = f.nxt(12 + j), sj = f.cur(12 + j), sj1 = f.cur(13 + j), sj5 = f.cur(17 + j);
             // sadd: out = ct + trivial(delta * s0)             constrains.rs:112-126, server_key.rs:78-83,104-114
             fe out = sj1;
-            if (j == 4) out = fe_add(out, fe_mul_small(s0, delta));
-            acc_sadd = fe_add(acc_sadd, fe_sub(snj, out));
+            if (j == 4) out = ar.add(out, ar.mul_small(s0, delta));
+            acc_sadd = ar.add(acc_sadd, ar.sub(snj, out));
             // add2: s_j + s_{5+j}                              constrains.rs:128-144, server_key.rs:89-102
-            acc_add2 = fe_add(acc_add2, fe_sub(snj, fe_add(sj, sj5)));
+            acc_add2 = ar.add(acc_add2, ar.sub(snj, ar.add(sj, sj5)));
             // smul: s0 * s_{1+j}                               constrains.rs:150-164, server_key.rs:116-124
-            acc_smul = fe_add(acc_smul, fe_sub(snj, fe_mul(sj1, s0)));
+            acc_smul = ar.add(acc_smul, ar.sub(snj, ar.mul(sj1, s0)));
         }
-        sink.put(4, fe_mul(f_sadd, acc_sadd));
-        sink.put(5, fe_mul(f_add2, acc_add2));
-        sink.put(7, fe_mul(f_smul, acc_smul));
+        sink.put(ar, 4, ar.mul(f_sadd, acc_sadd));
+        sink.put(ar, 5, ar.mul(f_add2, acc_add2));
+        sink.put(ar, 7, ar.mul(f_smul, acc_smul));
     }
     // r8..r11                                                 constrains.rs:166-180
     {
-        const fe d1 = fe_sub(sn1, s0);
-        sink.put(8, fe_mul(f_push, d1));
-        sink.put(9, fe_mul(f_read, d1));
-        sink.put(10, fe_mul(f_read2, fe_sub(f.nxt(17), s0)));
-        sink.put(11, fe_mul(f_noop, fe_sub(sn0, s0)));
+        const fe d1 = ar.sub(sn1, s0);
+        sink.put(ar, 8, ar.mul(f_push, d1));
+        sink.put(ar, 9, ar.mul(f_read, d1));
+        sink.put(ar, 10, ar.mul(f_read2, ar.sub(f.nxt(17), s0)));
+        sink.put(ar, 11, ar.mul(f_noop, ar.sub(sn0, s0)));
     }
     // Rescue round / copy                                     constrains.rs:182-216
     {
         const fe hash_flag = periodic[0];
         const fe h0 = f.cur(6);
-        const fe gate_round = fe_mul(hash_flag, h0);
-        const fe gate_copy = fe_mul(fe_sub(one, hash_flag), h0);
+        const fe gate_round = ar.mul(hash_flag, h0);
+        const fe gate_copy = ar.mul(ar.sub(one, hash_flag), h0);
         fe h[4] = {f.cur(7), f.cur(8), f.cur(9), f.cur(10)};
         fe hn[4] = {f.nxt(7), f.nxt(8), f.nxt(9), f.nxt(10)};
         // hash copy (r16..r19)
-        sink.put(16, fe_mul(fe_sub(hn[0], h[0]), gate_copy));
-        sink.put(17, fe_mul(fe_sub(hn[1], h[1]), gate_copy));
-        sink.put(18, fe_mul(hn[2], gate_copy));
-        sink.put(19, fe_mul(hn[3], gate_copy));
+        sink.put(ar, 16, ar.mul(ar.sub(hn[0], h[0]), gate_copy));
+        sink.put(ar, 17, ar.mul(ar.sub(hn[1], h[1]), gate_copy));
+        sink.put(ar, 18, ar.mul(hn[2], gate_copy));
+        sink.put(ar, 19, ar.mul(hn[3], gate_copy));
         // forward half: MDS * h^3 + ark[0..4], + opcode / pushed value
         fe c[4], step0[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) c[i] = fe_cube(h[i]);
-        rescue_mds(c, step0);
+        for (int i = 0; i < 4; i++) c[i] = ar.cube(h[i]);
+        rescue_mds(ar, c, step0);
 #pragma unroll
-        for (int i = 0; i < 4; i++) step0[i] = fe_add(step0[i], periodic[1 + i]);
+        for (int i = 0; i < 4; i++) step0[i] = ar.add(step0[i], periodic[1 + i]);
         // opcode = 16 b0 + 8 b1 + 4 b2 + 2 b3 + b4              flags.rs:81-87
-        fe opcode = fe_mul_small(b0, 16);
-        opcode = fe_add(opcode, fe_mul_small(b1, 8));
-        opcode = fe_add(opcode, fe_mul_small(b2, 4));
-        opcode = fe_add(opcode, fe_mul_small(b3, 2));
-        opcode = fe_add(opcode, b4);
-        step0[0] = fe_add(step0[0], opcode);
-        step0[1] = fe_add(step0[1], fe_mul(sn0, f_push));
+        fe opcode = ar.mul_small(b0, 16);
+        opcode = ar.add(opcode, ar.mul_small(b1, 8));
+        opcode = ar.add(opcode, ar.mul_small(b2, 4));
+        opcode = ar.add(opcode, ar.mul_small(b3, 2));
+        opcode = ar.add(opcode, b4);
+        step0[0] = ar.add(step0[0], opcode);
+        step0[1] = ar.add(step0[1], ar.mul(sn0, f_push));
         // backward half: (INV_MDS * (h' - ark[4..8]))^3
         fe d[4], step1[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) d[i] = fe_sub(hn[i], periodic[5 + i]);
-        rescue_inv_mds(k, d, step1);
+        for (int i = 0; i < 4; i++) d[i] = ar.sub(hn[i], periodic[5 + i]);
+        rescue_inv_mds(ar, k, d, step1);
 #pragma unroll
-        for (int i = 0; i < 4; i++) sink.put(12 + i, fe_mul(fe_sub(fe_cube(step1[i]), step0[i]), gate_round));
+        for (int i = 0; i < 4; i++) sink.put(ar, 12 + i, ar.mul(ar.sub(ar.cube(step1[i]), step0[i]), gate_round));
     }
 }
 

@@ -265,10 +265,8 @@ __device__ __forceinline__ fe fe_mul_flag(fe a, fe b, uint32_t& rare) {
 
 __device__ __forceinline__ fe fe_sqr(fe a) { return fe_mul(a, a); }
 
-// a * small (small < 2^32): 4 IMAD.WIDE + the small fold
-__device__ __forceinline__ fe fe_mul_small(fe a, uint32_t k) {
-    fe s;
-    uint32_t p0;
+// a * small (small < 2^32) = s + p0 * 2^128: 4 IMAD.WIDE
+__device__ __forceinline__ void fe_mul_small_raw(fe a, uint32_t k, fe& s, uint32_t& p0) {
     asm("{\n\t"
         ".reg .u32 t1, t3;\n\t"
         "mul.lo.u32 %0, %5, %9;\n\t"
@@ -285,7 +283,38 @@ __device__ __forceinline__ fe fe_mul_small(fe a, uint32_t k) {
         "}"
         : "=&r"(s.a0), "=&r"(s.a1), "=&r"(s.a2), "=&r"(s.a3), "=&r"(p0)
         : "r"(a.a0), "r"(a.a1), "r"(a.a2), "r"(a.a3), "r"(k));
+}
+__device__ __forceinline__ fe fe_mul_small(fe a, uint32_t k) {
+    fe s;
+    uint32_t p0;
+    fe_mul_small_raw(a, k, s, p0);
     return fe_fold_top(s, p0, 0);
+}
+
+// branch-free a * small, see fe_add_flag
+__device__ __forceinline__ fe fe_mul_small_flag(fe a, uint32_t k, uint32_t& rare);
+
+// Arithmetic policy of a straight-line block.  FAST: branch-free operations that only record their rare tails in
+// `rare`; the caller checks tainted() once and recomputes the block with the exact policy (a few times per proof).
+template <bool FAST>
+struct Arith {
+    uint32_t rare = 0;
+    __device__ __forceinline__ fe add(fe a, fe b) { return FAST ? fe_add_flag(a, b, rare) : fe_add(a, b); }
+    __device__ __forceinline__ fe sub(fe a, fe b) { return fe_sub(a, b); }
+    __device__ __forceinline__ fe mul(fe a, fe b) { return FAST ? fe_mul_flag(a, b, rare) : fe_mul(a, b); }
+    __device__ __forceinline__ fe sqr(fe a) { return mul(a, a); }
+    __device__ __forceinline__ fe cube(fe a) { return mul(mul(a, a), a); }
+    __device__ __forceinline__ fe mul_small(fe a, uint32_t k) { return FAST ? fe_mul_small_flag(a, k, rare) : fe_mul_small(a, k); }
+    __device__ __forceinline__ bool tainted() const { return FAST && rare == 0xFFFFFFFFu; }
+};
+
+__device__ __forceinline__ fe fe_mul_small_flag(fe a, uint32_t k, uint32_t& rare) {
+    fe s;
+    uint32_t p0, ov;
+    fe_mul_small_raw(a, k, s, p0);
+    s = fe_fold_top_raw(s, p0, 0, ov);
+    rare = max(rare, max(s.a3, 0u - ov));
+    return s;
 }
 
 __device__ __forceinline__ fe fe_pow(fe b, uint64_t e) {

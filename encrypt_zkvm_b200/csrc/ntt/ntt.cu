@@ -40,17 +40,6 @@ __device__ __forceinline__ fe tw_at(const uint4* __restrict__ tw, uint32_t log_s
     return fe_ldg(tw + (1u << log_size) + e);
 }
 
-// Arithmetic policy of a butterfly group.  FAST: branch-free operations that only record their rare tails in
-// `rare` (f128.cuh); the group is then recomputed with the exact policy, which happens a few times per proof.
-template <bool FAST>
-struct Arith {
-    uint32_t rare = 0;
-    __device__ __forceinline__ fe add(fe a, fe b) { return FAST ? fe_add_flag(a, b, rare) : fe_add(a, b); }
-    __device__ __forceinline__ fe sub(fe a, fe b) { return fe_sub(a, b); }
-    __device__ __forceinline__ fe mul(fe a, fe b) { return FAST ? fe_mul_flag(a, b, rare) : fe_mul(a, b); }
-    __device__ __forceinline__ bool tainted() const { return FAST && rare == 0xFFFFFFFFu; }
-};
-
 // b^e from a two-level table with the policy's product (see fe_tab_pow)
 template <class A>
 __device__ __forceinline__ fe tab_pow(A& ar, const uint4* __restrict__ tab, uint32_t e) {

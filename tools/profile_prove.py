@@ -1,6 +1,6 @@
 """One warm-up proof and one measured proof at 2^log_n rows (for ncu: skip the warm-up launches with --launch-skip).
 
-    python tools/profile_prove.py [log_n] [kind]
+    python tools/profile_prove.py [log_n] [kind]      # prints device ms, stage ms and per-kernel ms of the measured proof
 """
 import sys
 from pathlib import Path
@@ -16,12 +16,18 @@ prog, ex = ezk.synthetic_case(kind, log_n)
 trace = ex.trace()
 dev = torch.from_numpy(trace.view(np.int64)).to("cuda:0")
 torch.cuda.synchronize()
-with ezk.ExecutionProver(ezk.ProofOptions(), prog.hash(), ex.outputs(), ezk.ServerKey()) as p:
-    before = ezk.kernel_launch_count()
-    p.prove_device(dev.data_ptr(), 1 << log_n)
-    per_proof = ezk.kernel_launch_count() - before
-    p.timer_start()
-    proof = p.prove_device(dev.data_ptr(), 1 << log_n)
-    ms = p.timer_stop()
+p = ezk.ExecutionProver(ezk.ProofOptions(), prog.hash(), ex.outputs(), ezk.ServerKey())
+before = ezk.kernel_launch_count()
+p.prove_device(dev.data_ptr(), 1 << log_n)
+per_proof = ezk.kernel_launch_count() - before
+ezk.profile_enable(True)
+ezk.profile_reset()
+p.timer_start()
+proof = p.prove_device(dev.data_ptr(), 1 << log_n)
+ms = p.timer_stop()
+prof = ezk.profile_read()
+ezk.profile_enable(False)
 print(f"log_n={log_n} kernels_per_proof={per_proof} proof_bytes={len(proof)} device_ms={ms:.3f}")
-print({k: round(v, 3) for k, v in p.stage_times_ms().items()} if False else "")
+print("stages:", {k: round(v, 3) for k, v in p.stage_times_ms().items()})
+print("kernels:", {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])})
+p.close()
