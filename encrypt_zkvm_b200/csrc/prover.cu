@@ -127,6 +127,8 @@ GpuProver::GpuProver(int device) : device_(device) {
     EZK_CUDA(cudaMalloc(&d_flag_, sizeof(uint32_t)));
     for (auto& e : ev_) EZK_CUDA(cudaEventCreate(&e));
     for (auto& e : timer_ev_) EZK_CUDA(cudaEventCreate(&e));
+    EZK_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    for (auto& e : copy_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
 void GpuProver::timer_start() {
@@ -146,6 +148,8 @@ GpuProver::~GpuProver() {
     cudaSetDevice(device_);
     for (auto& e : ev_) cudaEventDestroy(e);
     for (auto& e : timer_ev_) cudaEventDestroy(e);
+    for (auto& e : copy_ev_) cudaEventDestroy(e);
+    cudaStreamDestroy(copy_stream_);
     cudaFree(d_flag_);
     cudaFree(d_params_);
     cudaFreeHost(pinned_);
@@ -256,19 +260,34 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
 
     // ---- (1) trace upload, interpolation, LDE, commitment ----
     mark();
-    const uint4* d_trace = device_trace;
-    if (host_columns) {
-        for (uint32_t c = 0; c < kWidth; c++)
-            EZK_CUDA(cudaMemcpyAsync(d_trace_in + (size_t)c * n, host_columns[c], n * 16, cudaMemcpyHostToDevice, stream_));
-        d_trace = d_trace_in;
-    }
-    mark();
     {
         NttScale sc{};
         put(sc.cvec[0], inverse(Fp::from_u64(n)));
         sc.chunk_shift = 63, sc.use_offset = 1;
-        ntt_columns(tables_, stream_, d_trace, n, d_tcoef, n, d_tmp, kWidth, log_n, true, &sc);
-        lde_columns(tables_, stream_, d_tcoef, n, d_tlde, L, d_tmp, kWidth, log_n);
+        if (host_columns) {
+            // Upload and transform in column groups: the copy of group k+1 (copy stream) overlaps the
+            // interpolation + LDE of group k (compute stream).  Columns are independent until the row hash.
+            constexpr uint32_t kGroup = 7;
+            EZK_CUDA(cudaEventRecord(copy_ev_[kWidth / kGroup], stream_));
+            EZK_CUDA(cudaStreamWaitEvent(copy_stream_, copy_ev_[kWidth / kGroup], 0));  // the arena may still be in use
+            for (uint32_t g = 0; g < kWidth / kGroup; g++) {
+                for (uint32_t c = g * kGroup; c < (g + 1) * kGroup; c++)
+                    EZK_CUDA(cudaMemcpyAsync(d_trace_in + (size_t)c * n, host_columns[c], n * 16, cudaMemcpyHostToDevice,
+                                             copy_stream_));
+                EZK_CUDA(cudaEventRecord(copy_ev_[g], copy_stream_));
+            }
+            for (uint32_t g = 0; g < kWidth / kGroup; g++) {
+                EZK_CUDA(cudaStreamWaitEvent(stream_, copy_ev_[g], 0));
+                if (g == 0) mark();
+                const size_t c0 = (size_t)g * kGroup;
+                ntt_columns(tables_, stream_, d_trace_in + c0 * n, n, d_tcoef + c0 * n, n, d_tmp, kGroup, log_n, true, &sc);
+                lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L, L, d_tmp, kGroup, log_n);
+            }
+        } else {
+            mark();
+            ntt_columns(tables_, stream_, device_trace, n, d_tcoef, n, d_tmp, kWidth, log_n, true, &sc);
+            lde_columns(tables_, stream_, d_tcoef, n, d_tlde, L, d_tmp, kWidth, log_n);
+        }
     }
     mark();
     merkle_hash_rows(stream_, d_tlde, L, kWidth, L, d_tnodes);

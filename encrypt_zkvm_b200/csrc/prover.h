@@ -56,6 +56,8 @@ private:
 
     int device_;
     cudaStream_t stream_ = nullptr;
+    cudaStream_t copy_stream_ = nullptr;  // host -> device trace upload, overlapped with the first transforms
+    cudaEvent_t copy_ev_[5];
     NttTables tables_;
     Arena arena_;
     uint8_t* pinned_ = nullptr;  // small host staging buffer
