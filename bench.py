@@ -190,23 +190,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from encrypt_zkvm_b200 import parallel
+
     def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return parallel.max_over_ranks(x, device="cuda")
 
     def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return parallel.sum_over_ranks(x, device="cuda")
 
     # ---- workload: host VM builds the trace (north star: trace generation stays on the host) ----
     n = 1 << args.log_n
-    prog, ex = ezk.synthetic_case(args.kind, args.log_n, seed=0xE2C0DE00 + args.log_n + 1000 * rank)
+    prog, ex = ezk.synthetic_case(args.kind, args.log_n, seed=parallel.unit_seed(0xE2C0DE00, args.log_n, rank))
     trace_np = ex.trace()
     program_hash, outputs = prog.hash(), ex.outputs()
     host = torch.from_numpy(trace_np.view(np.int64)).pin_memory()      # (28, n, 2) pinned
