@@ -53,7 +53,7 @@ class Program:
         return Program.compile(source)
 
     def __del__(self):
-        if getattr(self, "_handle", None) and self._handle.value:
+        if getattr(self, "_handle", None) and self._handle.value and lib is not None:
             lib.ezk_program_free(self._handle)
             self._handle = C.c_void_p()
 
@@ -92,7 +92,7 @@ class Execution:
         self._handle = handle
 
     def __del__(self):
-        if getattr(self, "_handle", None) and self._handle.value:
+        if getattr(self, "_handle", None) and self._handle.value and lib is not None:
             lib.ezk_execution_free(self._handle)
             self._handle = C.c_void_p()
 
