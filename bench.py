@@ -114,7 +114,7 @@ def scale_to_full(seconds_sample: float, sample_log_n: int, log_n: int) -> float
     return 1.0 / (seconds_sample * factor)
 
 
-def run_reference(args, rank: int):
+def run_reference(args, rank: int, out):
     """--impl reference: the reference's own CPU implementation of the path.  The Rust prover cannot be built here
     (no cargo/rustc, winterfell 0.9.0 not vendored), so this arm times the CPU oracle - the restated reference
     algorithm - with all host threads, on a bounded sample of the same workload."""
@@ -143,7 +143,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def workload_config(args) -> dict:
@@ -155,7 +155,17 @@ def workload_config(args) -> dict:
             "l2": "inputs larger than L2 (trace 28*n*16 B, LDE 8x that)"}
 
 
+def _claim_stdout():
+    """Everything the libraries print (NCCL's version banner goes to stdout) is sent to stderr; the returned file is
+    the real stdout, used only for the ONE JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -171,7 +181,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, out)
         return
 
     import numpy as np
@@ -301,7 +311,7 @@ def main():
         "stages": stages, "kernels": kernels, "proof_bytes": proof_bytes,
         "hbm_roofline_proofs_per_s": peak * 1e9 / sum(ab.values()),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
