@@ -27,8 +27,18 @@ namespace {
 
 constexpr uint32_t kTileElems = 4096;  // field elements staged per CTA (64 KiB): S points x lanes
 
-// lanes (independent transforms handled side by side so that global segments are 64..128 bytes)
-__host__ __device__ __forceinline__ uint32_t lanes_log_for(uint32_t log_s) { return log_s <= 9 ? 3u : 2u; }
+// lanes = independent transforms handled side by side by one CTA: enough of them to fill the 4096-element tile
+// (so that all 256 threads have a group of 8 in every step) and to make global segments 64..512 bytes
+__host__ __device__ __forceinline__ uint32_t lanes_log_for(uint32_t log_s) {
+    const uint32_t want = log_s >= 12 ? 0u : 12u - log_s;
+    return want < 2 ? 2u : (want > 5 ? 5u : want);
+}
+// threads of a CTA: one per group of 8 elements, at most 256
+inline unsigned threads_for(uint32_t log_s, uint32_t lanes_log, unsigned max_threads) {
+    const unsigned groups = (1u << (log_s - 3)) << lanes_log;
+    const unsigned t = groups < max_threads ? groups : max_threads;
+    return t < 32 ? 32 : t;
+}
 
 // w_8^1..3 for the in-register 8-point butterflies: [0] forward, [1] inverse
 __constant__ uint4 c_w8[2][4];
@@ -445,19 +455,19 @@ void ensure_smem_attr() {
 }
 void launch_strided(dim3 grid, size_t smem, cudaStream_t s, const StridedArgs& a) {
     if (g_variant == 1)
-        ntt_strided_pass<512, 2><<<grid, 512, smem, s>>>(a);
+        ntt_strided_pass<512, 2><<<grid, threads_for(a.log_s, a.lanes_log, 512), smem, s>>>(a);
     else if (g_variant == 2)
-        ntt_strided_pass<256, 2><<<grid, 256, smem, s>>>(a);
+        ntt_strided_pass<256, 2><<<grid, threads_for(a.log_s, a.lanes_log, 256), smem, s>>>(a);
     else
-        ntt_strided_pass<256, 3><<<grid, 256, smem, s>>>(a);
+        ntt_strided_pass<256, 3><<<grid, threads_for(a.log_s, a.lanes_log, 256), smem, s>>>(a);
 }
 void launch_final(dim3 grid, size_t smem, cudaStream_t s, const FinalArgs& a) {
     if (g_variant == 1)
-        ntt_final_pass<512, 2><<<grid, 512, smem, s>>>(a);
+        ntt_final_pass<512, 2><<<grid, threads_for(a.log_s, a.lanes_log, 512), smem, s>>>(a);
     else if (g_variant == 2)
-        ntt_final_pass<256, 2><<<grid, 256, smem, s>>>(a);
+        ntt_final_pass<256, 2><<<grid, threads_for(a.log_s, a.lanes_log, 256), smem, s>>>(a);
     else
-        ntt_final_pass<256, 3><<<grid, 256, smem, s>>>(a);
+        ntt_final_pass<256, 3><<<grid, threads_for(a.log_s, a.lanes_log, 256), smem, s>>>(a);
 }
 
 // strided passes p..2 over `ncols` arrays of n elements: the first pass reads `first_src` and writes `buf`,
@@ -618,7 +628,7 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
     a.dst = lde, a.dst_pitch = lde_pitch;
     a.log_n = log_n, a.log_s = pl.log_d[0], a.passes = pl.passes;
     a.log_top = pl.passes >= 2 ? pl.log_d[pl.passes - 1] : 0;
-    a.lanes_log = lanes_log_for(a.log_s);
+    a.lanes_log = lanes_log_for(a.log_s) > 3 ? 3 : lanes_log_for(a.log_s);  // lanes are cosets
     a.log_L = log_L;
     a.inv = 0;
     a.roots = t.root_fwd;
