@@ -58,6 +58,8 @@ SIGNATURES = {
                                           C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "ezk_prove": (C.c_int, [C.POINTER(EzkTrace), C.POINTER(EzkPublicInputs), C.POINTER(EzkOptions), C.POINTER(_P),
                             C.POINTER(C.c_size_t)]),
+    "ezk_comm_unique_id": (C.c_int, [_P]),
+    "ezk_prover_join": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "ezk_prover_stage_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "ezk_prover_timer_start": (C.c_int, [_P]),
     "ezk_prover_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float)]),

@@ -29,9 +29,9 @@ __device__ __forceinline__ fe root_pow_policy(A& ar, const uint4* __restrict__ t
     return ar.mul(a, b);
 }
 
-__global__ void __launch_bounds__(128) pair_inverse_kernel(const uint4* __restrict__ roots, uint32_t log_L, fe a, fe b,
-                                                           uint4* __restrict__ out) {
-    const uint64_t L = 1ull << log_L;
+__global__ void __launch_bounds__(128) pair_inverse_kernel(const uint4* __restrict__ roots, uint32_t log_L, RowShard sh,
+                                                           fe a, fe b, uint4* __restrict__ out) {
+    const uint64_t L = (1ull << log_L) >> sh.world_log;  // rows of this rank, packed index
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     fe pre[kBatch];
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128) pair_inverse_kernel(const uint4* __restri
         uint64_t i = t + q * nthreads;
         fe d = fe_one();
         if (i < L) {
-            fe x = domain_point(roots, log_L, i);
+            fe x = domain_point(roots, log_L, sh.global_row(i));
             d = fe_mul(fe_sub(x, a), fe_sub(x, b));
         }
         pre[q] = acc;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) pair_inverse_kernel(const uint4* __restri
         uint64_t i = t + q * nthreads;
         if (i < L) {
             // recompute d_i instead of keeping a second register array
-            fe x = domain_point(roots, log_L, i);
+            fe x = domain_point(roots, log_L, sh.global_row(i));
             fe d = fe_mul(fe_sub(x, a), fe_sub(x, b));
             fe_store(out + i, fe_mul(acc, pre[q]));
             acc = fe_mul(acc, d);
@@ -79,7 +79,7 @@ struct SumSink {
 template <bool FAST>
 __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, const uint4* __restrict__ lde, uint64_t pitch,
                                                uint32_t log_L, const ConstraintParams* __restrict__ p,
-                                               const uint4* __restrict__ inv_den, uint64_t i, fe& result) {
+                                               const uint4* __restrict__ inv_den, uint64_t packed, uint64_t i, fe& result) {
     const uint64_t L = 1ull << log_L;
     Arith<FAST> ar;
     LdeFrame f{lde, pitch, i, (i + 8) & (L - 1)};
@@ -105,16 +105,16 @@ __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, 
     for (int k = 12; k < 22; k++) s1 = ar.add(s1, ar.mul(ld2(p->bcoef[k]), ar.sub(f.cur(p->bcol[k]), ld2(p->bval[k]))));
     // B0/(x-1) + B1/(x-a) = (B0 (x-a) + B1 (x-1)) / ((x-1)(x-a))
     const fe num = ar.add(ar.mul(s0, ar.sub(x, a)), ar.mul(s1, ar.sub(x, fe_one())));
-    const fe bsum = ar.mul(num, fe_ldg(inv_den + i));
+    const fe bsum = ar.mul(num, fe_ldg(inv_den + packed));
     result = ar.add(t, bsum);
     return ar.tainted();
 }
 
 __device__ __noinline__ fe constraint_row_exact(const uint4* __restrict__ roots, const uint4* __restrict__ lde, uint64_t pitch,
                                                 uint32_t log_L, const ConstraintParams* __restrict__ p,
-                                                const uint4* __restrict__ inv_den, uint64_t i) {
+                                                const uint4* __restrict__ inv_den, uint64_t t, uint64_t i) {
     fe r;
-    constraint_row<false>(roots, lde, pitch, log_L, p, inv_den, i, r);
+    constraint_row<false>(roots, lde, pitch, log_L, p, inv_den, t, i, r);
     return r;
 }
 
@@ -122,15 +122,15 @@ template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) constraint_kernel(const uint4* __restrict__ roots, const uint4* __restrict__ lde,
                                                                    uint64_t pitch, uint32_t log_L,
                                                                    const ConstraintParams* __restrict__ p,
-                                                                   const uint4* __restrict__ inv_den,
+                                                                   const uint4* __restrict__ inv_den, RowShard sh,
                                                                    uint4* __restrict__ combined) {
-    const uint64_t L = 1ull << log_L;
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L) return;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ((1ull << log_L) >> sh.world_log)) return;
+    const uint64_t i = sh.global_row(t);
     fe r;
-    if (constraint_row<true>(roots, lde, pitch, log_L, p, inv_den, i, r))
-        r = constraint_row_exact(roots, lde, pitch, log_L, p, inv_den, i);
-    fe_store(combined + i, r);
+    if (constraint_row<true>(roots, lde, pitch, log_L, p, inv_den, t, i, r))
+        r = constraint_row_exact(roots, lde, pitch, log_L, p, inv_den, t, i);
+    fe_store(combined + t, r);
 }
 
 struct ArrayFrame {
@@ -160,22 +160,22 @@ __global__ void frames_kernel(const uint4* cur, const uint4* nxt, const uint4* p
 }  // namespace
 
 int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, uint32_t log_L, const uint64_t a[2], const uint64_t b[2],
-                        uint4* out) {
-    const uint64_t L = 1ull << log_L;
+                        uint4* out, RowShard sh) {
+    const uint64_t L = (1ull << log_L) >> sh.world_log;
     const unsigned threads = 128;
     uint64_t need = (L + kBatch - 1) / kBatch;
     unsigned blocks = (unsigned)((need + threads - 1) / threads);
     {
         LaunchScope ls(s, K_PAIR_INVERSE, L * 16);
-        pair_inverse_kernel<<<blocks, threads, 0, s>>>(root_fwd, log_L, fe_make(a[0], a[1]), fe_make(b[0], b[1]), out);
+        pair_inverse_kernel<<<blocks, threads, 0, s>>>(root_fwd, log_L, sh, fe_make(a[0], a[1]), fe_make(b[0], b[1]), out);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;
 }
 
 int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde, uint64_t pitch, uint32_t log_L,
-                         const ConstraintParams* params, const uint4* inv_den, uint4* combined) {
-    const uint64_t L = 1ull << log_L;
+                         const ConstraintParams* params, const uint4* inv_den, uint4* combined, RowShard sh) {
+    const uint64_t L = (1ull << log_L) >> sh.world_log;
     static int variant = -1;
     if (variant < 0) {
         const char* env = getenv("EZK_CONSTRAINT_VARIANT");
@@ -184,13 +184,13 @@ int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde
     {
         LaunchScope ls(s, K_CONSTRAINTS, L * 16 * (28 + 2));  // 28 columns + inv_den read, 1 column written
         if (variant == 1)
-            constraint_kernel<128, 3><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, combined);
+            constraint_kernel<128, 3><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
         else if (variant == 2)
-            constraint_kernel<128, 6><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, combined);
+            constraint_kernel<128, 6><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
         else if (variant == 3)
-            constraint_kernel<128, 8><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, combined);
+            constraint_kernel<128, 8><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
         else
-            constraint_kernel<128, 4><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, combined);
+            constraint_kernel<128, 4><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

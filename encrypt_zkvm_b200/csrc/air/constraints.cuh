@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "../common.h"
 
 namespace ezk {
 
@@ -21,13 +22,14 @@ struct ConstraintParams {  // device-resident, rebuilt for every proof (depends 
 };
 
 // out[i] = 1 / ((x_i - a)(x_i - b)),  x_i = 3 * w_L^i,  i < L = 2^log_L
+// (multi-GPU: out[t] for the packed rows t of this rank, x taken at global_row(t))
 int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, uint32_t log_L, const uint64_t a[2], const uint64_t b[2],
-                        uint4* out);
+                        uint4* out, RowShard sh = RowShard());
 
 // combined[i] = T_i / z_t(x_i) + B0_i / (x_i - 1) + B1_i / (x_i - g^(n-2))   
 // lde: column-major 28 x L; inv_den[i] = 1/((x_i - 1)(x_i - g^(n-2)))
 int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde, uint64_t pitch, uint32_t log_L,
-                         const ConstraintParams* params, const uint4* inv_den, uint4* combined);
+                         const ConstraintParams* params, const uint4* inv_den, uint4* combined, RowShard sh = RowShard());
 
 // parity helper: 20 transition values for explicit frames (cur/nxt: nframes x 28, periodic: nframes x 9, out: nframes x 20)
 int evaluate_frames(cudaStream_t s, const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,

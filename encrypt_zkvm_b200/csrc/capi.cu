@@ -151,6 +151,20 @@ int ezk_prover_stage_times(const ezk_prover* p, float* ms_out) {
     });
 }
 
+int ezk_comm_unique_id(uint8_t out[128]) {
+    return guarded([&] {
+        if (!out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        Comm::unique_id(out);
+    });
+}
+int ezk_prover_join(ezk_prover* p, int rank, int world, const uint8_t unique_id[128]) {
+    return guarded([&] {
+        if (!p || !unique_id) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->join(rank, world, unique_id);
+    });
+}
+
 int ezk_prover_timer_start(ezk_prover* p) {
     return guarded([&] {
         if (!p) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};

@@ -72,17 +72,18 @@ __global__ void __launch_bounds__(256) deep_combine_kernel(const uint4* __restri
 __global__ void __launch_bounds__(256) deep_pointwise_kernel(const uint4* __restrict__ roots,
                                                             const uint4* __restrict__ pq_lde, uint32_t log_L,
                                                             const uint4* __restrict__ inv_den, DeepScalars sc,
-                                                            uint4* __restrict__ deep) {
+                                                            RowShard sh, uint4* __restrict__ deep) {
     const uint64_t L = 1ull << log_L;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L) return;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (L >> sh.world_log)) return;
+    const uint64_t i = sh.global_row(t);
     fe w = fe_root_pow(roots, log_L, i);
     fe x = fe_add(fe_add(w, w), w);
     fe P = fe_ldg(pq_lde + i), Q = fe_ldg(pq_lde + L + i);
     fe t1 = fe_sub(fe_add(P, Q), fe_make(sc.s1[0], sc.s1[1]));
     fe t2 = fe_sub(P, fe_make(sc.s2[0], sc.s2[1]));
     fe num = fe_add(fe_mul(t1, fe_sub(x, fe_make(sc.zg[0], sc.zg[1]))), fe_mul(t2, fe_sub(x, fe_make(sc.z[0], sc.z[1]))));
-    fe_store(deep + i, fe_mul(num, fe_ldg(inv_den + i)));
+    fe_store(deep + t, fe_mul(num, fe_ldg(inv_den + t)));
 }
 
 __global__ void all_zero_kernel(const uint4* __restrict__ v, uint64_t count, uint32_t* flag) {
@@ -128,11 +129,11 @@ int deep_combine_coeffs(cudaStream_t s, const uint4* tcoeff, uint64_t tpitch, co
 }
 
 int deep_pointwise(cudaStream_t s, const uint4* root_fwd, const uint4* pq_lde, uint32_t log_L, const uint4* inv_den,
-                   DeepScalars sc, uint4* deep) {
-    const uint64_t L = 1ull << log_L;
+                   DeepScalars sc, uint4* deep, RowShard sh) {
+    const uint64_t L = (1ull << log_L) >> sh.world_log;
     {
         LaunchScope ls(s, K_DEEP_POINTWISE, L * 16 * 4);
-        deep_pointwise_kernel<<<(unsigned)((L + 255) / 256), 256, 0, s>>>(root_fwd, pq_lde, log_L, inv_den, sc, deep);
+        deep_pointwise_kernel<<<(unsigned)((L + 255) / 256), 256, 0, s>>>(root_fwd, pq_lde, log_L, inv_den, sc, sh, deep);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

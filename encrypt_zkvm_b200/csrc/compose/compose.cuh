@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "../common.h"
 
 namespace ezk {
 
@@ -26,7 +27,7 @@ struct DeepScalars {
     uint64_t z[2], zg[2], s1[2], s2[2];
 };
 int deep_pointwise(cudaStream_t s, const uint4* root_fwd, const uint4* pq_lde, uint32_t log_L, const uint4* inv_den,
-                   DeepScalars sc, uint4* deep);
+                   DeepScalars sc, uint4* deep, RowShard sh = RowShard());  // multi-GPU: packed rows of this rank
 
 // *flag |= 1 when any of the `count` elements is non-zero
 int check_all_zero(cudaStream_t s, const uint4* v, uint64_t count, uint32_t* flag);

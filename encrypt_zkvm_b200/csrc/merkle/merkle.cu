@@ -13,9 +13,11 @@ constexpr int kThreads = 256;
 
 // One thread per row; the table is column-major so a warp reads 32 consecutive 16-byte cells per column.
 __global__ void __launch_bounds__(kThreads) hash_rows_kernel(const uint4* __restrict__ table, uint64_t pitch,
-                                                            uint32_t width, uint64_t rows, uint4* __restrict__ leaves) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
+                                                            uint32_t width, uint64_t rows, RowShard sh,
+                                                            uint4* __restrict__ leaves) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows) return;
+    const uint64_t i = sh.global_row(t);
     uint32_t cv[8];
     b3_init(cv);
     const uint32_t nblocks = (width + 3) / 4;
@@ -31,8 +33,21 @@ __global__ void __launch_bounds__(kThreads) hash_rows_kernel(const uint4* __rest
         uint32_t flags = (b == 0 ? B3_CHUNK_START : 0u) | (b == nblocks - 1 ? (B3_CHUNK_END | B3_ROOT) : 0u);
         b3_compress(cv, m, cells * 16, flags);
     }
-    leaves[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
-    leaves[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+    leaves[2 * t] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    leaves[2 * t + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+// dst[global_row_q(t) * UNITS + u] = src[(q * per_rank + t) * UNITS + u]: puts the all-gathered per-rank blocks
+// (packed row order) back into natural row order.  UNITS = 16-byte words per item (1 element, 2 digest).
+template <int UNITS>
+__global__ void unpack_rows_kernel(const uint4* __restrict__ src, uint64_t per_rank, uint32_t world_log, uint4* __restrict__ dst) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (per_rank << world_log)) return;
+    RowShard sh;
+    sh.rank = (uint32_t)(g / per_rank), sh.world_log = world_log;
+    const uint64_t i = sh.global_row(g % per_rank);
+#pragma unroll
+    for (int u = 0; u < UNITS; u++) dst[i * UNITS + u] = src[g * UNITS + u];
 }
 
 // parents k in [level, 2*level): nodes[k] = merge(nodes[2k], nodes[2k+1])
@@ -79,10 +94,29 @@ __global__ void gather_digests_kernel(const uint4* __restrict__ nodes, const uin
 }  // namespace
 
 int merkle_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t rows, uint4* nodes) {
-    unsigned blocks = (unsigned)((rows + kThreads - 1) / kThreads);
+    return hash_rows_sharded(s, table, pitch, width, rows, RowShard(), nodes + 2 * rows);
+}
+
+int hash_rows_sharded(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard sh,
+                      uint4* digests) {
+    unsigned blocks = (unsigned)((local_rows + kThreads - 1) / kThreads);
     {
-        LaunchScope ls(s, K_HASH_ROWS, rows * ((uint64_t)width * 16 + 32));
-        hash_rows_kernel<<<blocks, kThreads, 0, s>>>(table, pitch, width, rows, nodes + 2 * rows);
+        LaunchScope ls(s, K_HASH_ROWS, local_rows * ((uint64_t)width * 16 + 32));
+        hash_rows_kernel<<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
+    }
+    EZK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+int unpack_rows(cudaStream_t s, const uint4* gathered, uint64_t per_rank, uint32_t world_log, uint32_t units, uint4* dst) {
+    const uint64_t total = per_rank << world_log;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    {
+        LaunchScope ls(s, K_GATHER, total * units * 32);
+        if (units == 2)
+            unpack_rows_kernel<2><<<blocks, 256, 0, s>>>(gathered, per_rank, world_log, dst);
+        else
+            unpack_rows_kernel<1><<<blocks, 256, 0, s>>>(gathered, per_rank, world_log, dst);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "../common.h"
 
 namespace ezk {
 
@@ -12,6 +13,11 @@ namespace ezk {
 
 // leaf i = blake3(row i as little-endian bytes), row i = (table[c * pitch + i])_{c < width}
 int merkle_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t rows, uint4* nodes);
+// multi-GPU: digests[t] = blake3(row global_row(t)) for the local_rows rows this rank owns (packed order)
+int hash_rows_sharded(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard sh,
+                      uint4* digests);
+// dst[global_row_q(t)] = gathered[q][t] for the 2^world_log all-gathered blocks of per_rank items (units x 16 bytes each)
+int unpack_rows(cudaStream_t s, const uint4* gathered, uint64_t per_rank, uint32_t world_log, uint32_t units, uint4* dst);
 // builds all internal nodes from the leaves already stored in nodes[num_leaves..2*num_leaves)
 int merkle_build(cudaStream_t s, uint4* nodes, uint64_t num_leaves);
 

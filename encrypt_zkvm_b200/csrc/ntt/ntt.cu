@@ -248,7 +248,8 @@ struct StridedArgs {
     uint64_t src_pitch, dst_pitch;  // per grid.y column, in elements
     uint32_t log_stride, log_s;     // stride = lo range, S = n_i
     uint32_t lanes_log;
-    uint32_t coset_first;           // LDE first pass: column y reads coefficient column y/8, scaled by w_L^(c*m), c = y%8
+    uint32_t coset_first;           // LDE first pass: column y reads coefficient column y / nc, scaled by w_L^(c*m),
+    uint32_t cs_log, cs_base, cs_step;  //   nc = 1 << cs_log cosets per column, c = cs_base + cs_step * (y % nc)
     uint32_t log_L;
     uint32_t inv;
     const uint4* roots;             // two-level 2^28-th root table (forward or inverse)
@@ -292,8 +293,8 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_strided_pass(StridedArgs a)
     P.base = P.lo0 + (hi << (a.log_stride + a.log_s));
     const uint32_t col = blockIdx.y;
     if (a.coset_first) {
-        P.coset = col & 7;
-        P.src = a.src + (uint64_t)(col >> 3) * a.src_pitch;
+        P.coset = a.cs_base + a.cs_step * (col & ((1u << a.cs_log) - 1));
+        P.src = a.src + (uint64_t)(col >> a.cs_log) * a.src_pitch;
     } else {
         P.coset = 0;
         P.src = a.src + (uint64_t)col * a.src_pitch;
@@ -318,6 +319,7 @@ struct FinalArgs {
     uint32_t lanes_log;             // 0 (one run per tile), 2 or 3
     uint32_t log_L;
     uint32_t inv;
+    uint32_t cs_log, cs_base, cs_step;  // LDE: 1 << cs_log cosets are computed, coset k = cs_base + cs_step * k
     const uint4* roots;
     const uint4* tw;
     const uint4* off_tab;
@@ -333,15 +335,16 @@ struct FinalPass {
     template <class A>
     __device__ __forceinline__ fe load(A& ar, uint32_t lane, uint32_t m) const {
         if (a->mode == 0) return fe_load(src + ((run0 + lane * run_step) << a->log_s) + m);
-        const uint32_t coset = coset0 + lane;
-        if (a->mode == 1) return fe_load(src + (uint64_t)coset * a->src_pitch + (run0 << a->log_s) + m);
+        // coset0 + lane = index into this prover's coset list; the coset itself is cs_base + cs_step * index
+        if (a->mode == 1) return fe_load(src + (uint64_t)(coset0 + lane) * a->src_pitch + (run0 << a->log_s) + m);
+        const uint32_t coset = a->cs_base + a->cs_step * (coset0 + lane);
         fe v = fe_load(src + m);
         if (coset != 0) v = ar.mul(v, root_pow(ar, a->roots, a->log_L, (uint64_t)coset * m));
         return v;
     }
     __device__ __forceinline__ uint64_t out_index(uint32_t lane, uint32_t j1) const {
         if (a->mode == 0) return ((uint64_t)j1 << log_H) + out_base + lane;
-        return ((((uint64_t)j1 << log_H) + out_base) << 3) + coset0 + lane;
+        return ((((uint64_t)j1 << log_H) + out_base) << 3) + a->cs_base + a->cs_step * (coset0 + lane);
     }
     template <class A>
     __device__ __forceinline__ fe finish(A& ar, uint32_t lane, uint32_t j1, fe v) const {
@@ -382,12 +385,12 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_final_pass(const __grid_con
             P.out_base = (rest << a.log_top) + jp0;  // j_p + n_p * rest
         }
     } else {
-        // LDE: one run per tile, the lanes are cosets (all 8, or one half of them when lanes = 4)
-        const uint32_t halves_log = 3 - a.lanes_log;
+        // LDE: one run per tile, the lanes are cosets (all of this prover's, or a part of them)
+        const uint32_t halves_log = a.cs_log - a.lanes_log;
         const uint64_t hp = blockIdx.x >> halves_log;
         P.coset0 = (blockIdx.x & ((1u << halves_log) - 1)) << a.lanes_log;
         P.run0 = hp, P.run_step = 0;
-        P.src = a.mode == 1 ? a.src + (uint64_t)col * 8 * a.src_pitch : a.src + (uint64_t)col * a.src_pitch;
+        P.src = a.mode == 1 ? a.src + (((uint64_t)col * a.src_pitch) << a.cs_log) : a.src + (uint64_t)col * a.src_pitch;
         if (a.passes <= 1) {
             P.out_base = 0;
         } else {
@@ -474,7 +477,7 @@ void launch_final(dim3 grid, size_t smem, cudaStream_t s, const FinalArgs& a) {
 // later passes run in place in `buf`.  With `coset` the first pass reads coefficient column y/8 and applies the
 // coset factor w_L^(c*m), c = y%8 (LDE).
 int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log_n, bool inverse, const uint4* first_src,
-                uint64_t first_src_pitch, bool coset, uint4* buf, uint64_t buf_pitch, uint32_t ncols, uint32_t log_L) {
+                uint64_t first_src_pitch, const CosetSet* cs, uint4* buf, uint64_t buf_pitch, uint32_t ncols, uint32_t log_L) {
     int launches = 0;
     uint32_t log_stride = log_n;
     for (int i = (int)pl.passes - 1; i >= 1; i--) {
@@ -487,7 +490,8 @@ int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log
         a.log_stride = log_stride, a.log_s = pl.log_d[i];
         a.lanes_log = lanes_log_for(a.log_s);
         if (a.lanes_log > log_stride) a.lanes_log = log_stride;
-        a.coset_first = (first && coset) ? 1 : 0;
+        a.coset_first = (first && cs) ? 1 : 0;
+        if (cs) a.cs_log = cs->count_log, a.cs_base = cs->base, a.cs_step = cs->step;
         a.log_L = log_L;
         a.inv = inverse ? 1 : 0;
         a.roots = inverse ? t.root_inv : t.root_fwd;
@@ -497,7 +501,7 @@ int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log
             // compulsory traffic: every element of every column read once and written once (the 8 coset copies of
             // an LDE first pass share one read of the coefficient column)
             const uint64_t elems = (uint64_t)ncols << log_n;
-            LaunchScope ls(s, K_NTT_STRIDED, (a.coset_first ? elems / 8 + elems : 2 * elems) * 16);
+            LaunchScope ls(s, K_NTT_STRIDED, (a.coset_first ? (elems >> cs->count_log) + elems : 2 * elems) * 16);
             launch_strided(grid, tile_bytes(a.log_s, a.lanes_log), s, a);
         }
         EZK_CUDA(cudaGetLastError());
@@ -590,7 +594,7 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
     int launches = 0;
     FinalArgs a{};
     if (pl.passes >= 2) {
-        launches = run_strided(t, s, pl, log_n, inverse, src, src_pitch, false, work, n, ncols, 0);
+        launches = run_strided(t, s, pl, log_n, inverse, src, src_pitch, nullptr, work, n, ncols, 0);
         a.src = work, a.src_pitch = n;
     } else {
         a.src = src, a.src_pitch = src_pitch;
@@ -617,9 +621,10 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
 }
 
 int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t coeff_pitch, uint4* lde,
-                uint64_t lde_pitch, uint4* tmp, uint32_t ncols, uint32_t log_n) {
+                uint64_t lde_pitch, uint4* tmp, uint32_t ncols, uint32_t log_n, CosetSet cs) {
     ensure_smem_attr();
     if (log_n < 3) throw CudaError("lde_columns: n must be at least 8");
+    if (cs.count_log > 3 || cs.base + cs.step * ((1u << cs.count_log) - 1) > 7) throw CudaError("lde_columns: bad coset set");
     Plan pl = make_plan(log_n, t.max_tile_log);
     const uint64_t n = 1ull << log_n;
     const uint32_t log_L = log_n + 3;
@@ -628,7 +633,8 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
     a.dst = lde, a.dst_pitch = lde_pitch;
     a.log_n = log_n, a.log_s = pl.log_d[0], a.passes = pl.passes;
     a.log_top = pl.passes >= 2 ? pl.log_d[pl.passes - 1] : 0;
-    a.lanes_log = lanes_log_for(a.log_s) > 3 ? 3 : lanes_log_for(a.log_s);  // lanes are cosets
+    a.lanes_log = lanes_log_for(a.log_s) > cs.count_log ? cs.count_log : lanes_log_for(a.log_s);  // lanes are cosets
+    a.cs_log = cs.count_log, a.cs_base = cs.base, a.cs_step = cs.step;
     a.log_L = log_L;
     a.inv = 0;
     a.roots = t.root_fwd;
@@ -638,14 +644,14 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
         a.mode = 2;
         a.src = coeff, a.src_pitch = coeff_pitch;
     } else {
-        launches += run_strided(t, s, pl, log_n, false, coeff, coeff_pitch, true, tmp, n, ncols * 8, log_L);
+        launches += run_strided(t, s, pl, log_n, false, coeff, coeff_pitch, &cs, tmp, n, ncols << cs.count_log, log_L);
         a.mode = 1;
         a.src = tmp, a.src_pitch = n;
     }
-    dim3 grid((unsigned)((1ull << (log_n - pl.log_d[0])) << (3 - a.lanes_log)), ncols);
+    dim3 grid((unsigned)((1ull << (log_n - pl.log_d[0])) << (cs.count_log - a.lanes_log)), ncols);
     {
-        const uint64_t elems = (uint64_t)ncols << log_n;
-        LaunchScope ls(s, K_NTT_FINAL, (pl.passes == 1 ? elems + 8 * elems : 16 * elems) * 16);
+        const uint64_t elems = (uint64_t)ncols << log_n, outs = elems << cs.count_log;
+        LaunchScope ls(s, K_NTT_FINAL, (pl.passes == 1 ? elems + outs : 2 * outs) * 16);
         launch_final(grid, tile_bytes(a.log_s, a.lanes_log), s, a);
     }
     EZK_CUDA(cudaGetLastError());

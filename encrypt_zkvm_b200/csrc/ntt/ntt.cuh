@@ -37,10 +37,17 @@ struct NttScale {
 int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t src_pitch, uint4* dst, uint64_t dst_pitch,
                 uint4* work, uint32_t ncols, uint32_t log_n, bool inverse, const NttScale* scale);
 
+// Which of the 8 LDE cosets a prover computes: coset k = base + step * k, k < 1 << count_log.  {3, 0, 1} = all of
+// them (single GPU); rank r of G = 2^g ranks owns {r, r + G, ...} = {3 - g, r, G}.
+struct CosetSet {
+    uint32_t count_log = 3, base = 0, step = 1;
+};
+
 // Coset low-degree extension with blowup 8: coeff[c][m] must already be scaled by o^m; writes
 // lde[c][8j + k] = sum_m coeff[c][m] * (w_L^k)^m * w_n^(mj)   (natural order over the LDE domain o*<w_L>).
-// tmp must hold ncols * 8 * n elements when n > 2^max_tile_log (unused otherwise).
+// Only the rows of the cosets in `cs` are written (the others are left untouched).
+// tmp must hold ncols * (number of cosets) * n elements when n > 2^max_tile_log (unused otherwise).
 int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t coeff_pitch, uint4* lde,
-                uint64_t lde_pitch, uint4* tmp, uint32_t ncols, uint32_t log_n);
+                uint64_t lde_pitch, uint4* tmp, uint32_t ncols, uint32_t log_n, CosetSet cs = CosetSet());
 
 }  // namespace ezk

@@ -131,6 +131,12 @@ GpuProver::GpuProver(int device) : device_(device) {
     for (auto& e : copy_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
+void GpuProver::join(int rank, int world, const uint8_t id[128]) {
+    EZK_CUDA(cudaSetDevice(device_));
+    sync();
+    comm_.init(rank, world, id);
+}
+
 void GpuProver::timer_start() {
     EZK_CUDA(cudaSetDevice(device_));
     EZK_CUDA(cudaEventRecord(timer_ev_[0], stream_));
@@ -210,7 +216,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         }
         fri_elems += 8192;
     }
-    const size_t need = 2 * kWidth * n + 2 * kWidth * L + 4 * L + 3 * L + kCompCols * L + 4 * L + 2 * n + 2 * L + L +
+    const size_t need = 2 * kWidth * n + 2 * kWidth * L + 4 * L + 3 * L + kCompCols * L + 4 * L + 2 * n + 2 * L + L + 4 * L +
                         (size_t)(2 * kWidth + kCompCols) * eval_blocks + fri_elems + 65536;
     reserve(need);
     reset_arena();
@@ -229,6 +235,29 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     uint4* d_deep = alloc(L);
     uint4* d_scratch = alloc((size_t)(2 * kWidth + kCompCols) * eval_blocks);
     uint4* d_small = alloc(4096);  // OOD outputs, deep coefficients, query staging
+    // multi-GPU: this rank's packed rows (digests or elements) and the all-gathered blocks of every rank
+    const bool sharded = comm_.active();
+    const RowShard sh{(uint32_t)comm_.rank(), comm_.world_log()};
+    const CosetSet cs{3 - comm_.world_log(), (uint32_t)comm_.rank(), (uint32_t)comm_.world()};
+    const uint64_t L_local = L >> comm_.world_log();
+    uint4* d_pack = sharded ? alloc(2 * L_local) : nullptr;
+    uint4* d_allg = sharded ? alloc(2 * L) : nullptr;
+    // items of `units` 16-byte words per owned row in d_pack -> natural row order in dst, on every rank
+    auto share_rows = [&](uint32_t units, uint4* dst) {
+        comm_.all_gather(d_pack, d_allg, L_local * units * 16, stream_);
+        count_launch();
+        unpack_rows(stream_, d_allg, L_local, comm_.world_log(), units, dst);
+    };
+    // leaf digests of a column-major table over the LDE domain -> nodes[L..2L)
+    auto commit_rows = [&](const uint4* table, uint32_t width, uint4* nodes) {
+        if (!sharded) {
+            merkle_hash_rows(stream_, table, L, width, L, nodes);
+        } else {
+            hash_rows_sharded(stream_, table, L, width, L_local, sh, d_pack);
+            share_rows(2, nodes + 2 * L);
+        }
+        merkle_build(stream_, nodes, L);
+    };
     last_ = Last{};
     last_.n = n, last_.L = L, last_.tlde = d_tlde, last_.clde = d_clde, last_.tcoef = d_tcoef;
     last_.combined_copy = d_combined, last_.deep = d_deep;
@@ -281,17 +310,16 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
                 if (g == 0) mark();
                 const size_t c0 = (size_t)g * kGroup;
                 ntt_columns(tables_, stream_, d_trace_in + c0 * n, n, d_tcoef + c0 * n, n, d_tmp, kGroup, log_n, true, &sc);
-                lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L, L, d_tmp, kGroup, log_n);
+                lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L, L, d_tmp, kGroup, log_n, cs);
             }
         } else {
             mark();
             ntt_columns(tables_, stream_, device_trace, n, d_tcoef, n, d_tmp, kWidth, log_n, true, &sc);
-            lde_columns(tables_, stream_, d_tcoef, n, d_tlde, L, d_tmp, kWidth, log_n);
+            lde_columns(tables_, stream_, d_tcoef, n, d_tlde, L, d_tmp, kWidth, log_n, cs);
         }
     }
     mark();
-    merkle_hash_rows(stream_, d_tlde, L, kWidth, L, d_tnodes);
-    merkle_build(stream_, d_tnodes, L);
+    commit_rows(d_tlde, kWidth, d_tnodes);
     last_.trace_root = root_of(d_tnodes);
     commitments.insert(commitments.end(), last_.trace_root.begin(), last_.trace_root.end());
     coin.reseed(last_.trace_root);
@@ -348,8 +376,9 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         h2d(d_params_, &hp, sizeof(hp));
         uint64_t a[2], b[2];
         put(a, Fp(1)), put(b, g_last);
-        domain_pair_inverse(stream_, tables_.root_fwd, log_L, a, b, d_invden);
-        evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_invden, d_combined);
+        domain_pair_inverse(stream_, tables_.root_fwd, log_L, a, b, d_invden, sh);
+        evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_invden, sharded ? d_pack : d_combined, sh);
+        if (sharded) share_rows(1, d_combined);
     }
     mark();
 
@@ -371,9 +400,8 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         if (flag)
             throw ProveFailure{EZK_ERR_CONSTRAINT_DEGREE,
                                "constraint composition polynomial has degree >= 7n: the trace does not satisfy the AIR"};
-        lde_columns(tables_, stream_, d_ccoef, n, d_clde, L, d_tmp, kCompCols, log_n);
-        merkle_hash_rows(stream_, d_clde, L, kCompCols, L, d_cnodes);
-        merkle_build(stream_, d_cnodes, L);
+        lde_columns(tables_, stream_, d_ccoef, n, d_clde, L, d_tmp, kCompCols, log_n, cs);
+        commit_rows(d_clde, kCompCols, d_cnodes);
         last_.comp_root = root_of(d_cnodes);
         commitments.insert(commitments.end(), last_.comp_root.begin(), last_.comp_root.end());
         coin.reseed(last_.comp_root);
@@ -409,13 +437,14 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         uint4* d_dc = d_small + 128;
         h2d(d_dc, dc.data(), dc.size() * 16);
         deep_combine_coeffs(stream_, d_tcoef, n, d_ccoef, n, log_n, d_dc, d_pq);
-        lde_columns(tables_, stream_, d_pq, n, d_pqlde, L, d_tmp, 2, log_n);
+        lde_columns(tables_, stream_, d_pq, n, d_pqlde, L, d_tmp, 2, log_n, cs);
         uint64_t a[2], b[2];
         put(a, z), put(b, zg);
-        domain_pair_inverse(stream_, tables_.root_fwd, log_L, a, b, d_invden);
+        domain_pair_inverse(stream_, tables_.root_fwd, log_L, a, b, d_invden, sh);
         DeepScalars ds;
         put(ds.z, z), put(ds.zg, zg), put(ds.s1, s1), put(ds.s2, s2);
-        deep_pointwise(stream_, tables_.root_fwd, d_pqlde, log_L, d_invden, ds, d_deep);
+        deep_pointwise(stream_, tables_.root_fwd, d_pqlde, log_L, d_invden, ds, sharded ? d_pack : d_deep, sh);
+        if (sharded) share_rows(1, d_deep);
     }
     mark();
 
@@ -495,8 +524,10 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     uint64_t* d_idx = reinterpret_cast<uint64_t*>(alloc(8192));  // up to 16384 u64 indices
     uint4* d_gather = alloc(32768);
     // rows at `pos` from a column-major table + batch Merkle proof over `nodes`
+    // `rows_sharded`: the table holds only this rank's LDE rows (multi-GPU), so every opened row is taken from
+    // the all-gathered copy of its owner; the Merkle nodes are replicated on every rank.
     auto write_opening = [&](const uint4* table, uint64_t pitch, uint32_t width, const uint4* nodes, uint64_t num_leaves,
-                             const std::vector<uint64_t>& pos) {
+                             const std::vector<uint64_t>& pos, bool rows_sharded) {
         const uint32_t nq = (uint32_t)pos.size();
         auto idx_lists = batch_proof_node_indices(num_leaves, pos);
         std::vector<uint64_t> flat(pos);
@@ -510,6 +541,15 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         std::vector<uint8_t> host((size_t)nq * width * 16 + ndig * 32);
         d2h(host.data(), d_gather, host.size());
         const size_t vbytes = (size_t)nq * width * 16;
+        if (rows_sharded) {
+            comm_.all_gather(d_gather, d_allg, vbytes, stream_);
+            count_launch();
+            std::vector<uint8_t> all(vbytes * comm_.world());
+            d2h(all.data(), d_allg, all.size());
+            for (uint32_t q = 0; q < nq; q++)
+                memcpy(host.data() + (size_t)q * width * 16, all.data() + sh.owner(pos[q]) * vbytes + (size_t)q * width * 16,
+                       (size_t)width * 16);
+        }
         w.u32((uint32_t)vbytes);
         w.bytes(host.data(), vbytes);
         std::vector<uint8_t> paths;
@@ -523,8 +563,8 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         w.u32((uint32_t)paths.size());
         w.bytes(paths.data(), paths.size());
     };
-    write_opening(d_tlde, L, kWidth, d_tnodes, L, positions);
-    write_opening(d_clde, L, kCompCols, d_cnodes, L, positions);
+    write_opening(d_tlde, L, kWidth, d_tnodes, L, positions, sharded);
+    write_opening(d_clde, L, kCompCols, d_cnodes, L, positions, sharded);
     // OodFrame
     w.u16((uint16_t)(1 + ood_trace.size() * 16));
     w.u8(2);
@@ -539,7 +579,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         for (auto& layer : layers) {
             pos = fold_positions(pos, layer.size, 8);
             const uint64_t m = layer.size / 8;
-            write_opening(layer.evals, m, 8, layer.nodes, m, pos);
+            write_opening(layer.evals, m, 8, layer.nodes, m, pos, false);
         }
     }
     w.u16((uint16_t)(remainder.size() * 16));

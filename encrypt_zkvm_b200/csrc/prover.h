@@ -2,6 +2,7 @@
 // Drop-in for `ExecutionProver::prove` (prover/src/lib.rs:40-77, called at vm/src/lib.rs:26).
 #pragma once
 #include "air/constraints.cuh"
+#include "dist/comm.h"
 #include "host/transcript.h"
 #include "ntt/ntt.cuh"
 #include <string>
@@ -28,6 +29,12 @@ public:
     // host columns (28 pointers) or device-resident trace; exactly one of them non-null
     std::vector<uint8_t> prove(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
                                const PublicInputs& pub, const ProofOptions& opt);
+
+    // Multi-GPU single proof: after join(), prove() must be called by every rank of the group with the
+    // same trace, public inputs and options; each rank extends / evaluates / hashes the LDE cosets it owns, the
+    // per-row products are all-gathered over NCCL, and every rank returns the same proof bytes.
+    void join(int rank, int world, const uint8_t unique_id[128]);
+    int world() const { return comm_.world(); }
 
     const float* stage_ms() const { return stage_ms_; }
     void timer_start();
@@ -59,6 +66,7 @@ private:
     cudaStream_t copy_stream_ = nullptr;  // host -> device trace upload, overlapped with the first transforms
     cudaEvent_t copy_ev_[5];
     NttTables tables_;
+    Comm comm_;
     Arena arena_;
     uint8_t* pinned_ = nullptr;  // small host staging buffer
     size_t pinned_bytes_ = 0;

@@ -183,6 +183,23 @@ class ExecutionProver:
                                          C.byref(out), C.byref(out_len))
         return self._finish(rc, out, out_len)
 
+    # -- multi-GPU single proof -------------------------------------------------------------------------
+    def join_group(self) -> int:
+        """Shards every following prove() over the ranks of the default torch.distributed group (1, 2, 4 or 8
+        GPUs of one box).  Collective: every rank must call it, then call prove() with the same inputs."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = C.create_string_buffer(128)
+        if rank == 0:
+            check(lib.ezk_comm_unique_id(ident))
+        box = [ident.raw]
+        dist.broadcast_object_list(box, src=0)
+        check(lib.ezk_prover_join(self._handle, rank, world, box[0]))
+        return world
+
+    def leave_group(self) -> None:
+        check(lib.ezk_prover_join(self._handle, 0, 1, bytes(128)))
+
     # -- timing -----------------------------------------------------------------------------------------
     def timer_start(self) -> None:
         check(lib.ezk_prover_timer_start(self._handle))

@@ -87,6 +87,16 @@ int ezk_prover_prove_device(ezk_prover* p, const void* d_trace, uint64_t length,
 int ezk_prove(const ezk_trace* trace, const ezk_public_inputs* pub, const ezk_options* opt, uint8_t** proof,
               size_t* proof_len);
 
+/* ---- one proof sharded over the GPUs of a box (no reference counterpart: the reference is one thread) ----
+ * One process per GPU.  Rank 0 calls ezk_comm_unique_id and hands the 128 bytes to the other ranks (any
+ * transport; the Python binding uses torch.distributed); every rank then calls ezk_prover_join on its own
+ * prover (a collective: it builds the NCCL communicator).  From then on ezk_prover_prove must be called by ALL
+ * ranks with the same trace / public inputs / options: rank r extends, evaluates and hashes the LDE cosets
+ * {c : c mod world = r}, the per-row products travel over NVLink (ncclAllGather), and every rank returns the
+ * same proof bytes, identical to the single-GPU proof.  world in {1, 2, 4, 8}; world = 1 leaves the group. */
+int ezk_comm_unique_id(uint8_t out[128]);
+int ezk_prover_join(ezk_prover* p, int rank, int world, const uint8_t unique_id[128]);
+
 /* Device-time of the stages of the last proof, milliseconds (CUDA events on the prover's stream). */
 enum ezk_stage {
     EZK_STAGE_UPLOAD = 0,     /* host -> device trace copy */

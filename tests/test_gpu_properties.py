@@ -140,3 +140,19 @@ def test_host_and_device_traces_give_identical_bytes_2p18(gpu_prover_factory):
         torch.cuda.synchronize()
         dev = p.prove_device(d.data_ptr(), case.trace.shape[1]).to_bytes()
     assert host == dev
+
+
+def test_sharded_proof_is_byte_identical_on_two_gpus(gpu_prover_factory):
+    """one proof sharded by LDE coset over 2 GPUs (NCCL all-gathers of digests / evaluations) gives the
+    same bytes as the single-GPU proof.  Needs a box with >= 2 GPUs; skipped otherwise."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    if gpu_prover_factory.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", str(root / "tools" / "sharded_check.py"),
+                        "7", "10", "13"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count('"identical": true') == 3
