@@ -9,7 +9,7 @@ using namespace dev;
 
 namespace {
 
-constexpr int kBatch = 16;  // elements per thread in Montgomery batch inversion
+constexpr int kBatch = 64;  // elements per thread in Montgomery batch inversion
 
 __device__ __forceinline__ fe ld2(const uint64_t v[2]) { return fe_make(v[0], v[1]); }
 
@@ -29,34 +29,35 @@ __device__ __forceinline__ fe root_pow_policy(A& ar, const uint4* __restrict__ t
     return ar.mul(a, b);
 }
 
-__global__ void __launch_bounds__(128) pair_inverse_kernel(const uint4* __restrict__ roots, uint32_t log_L, RowShard sh,
-                                                           fe a, fe b, uint4* __restrict__ out) {
+// out[u] = 1 / ((x - a)(x - b)) at x = 3 w_L^(global_row(u)), u < L / world.  Montgomery batch inversion with
+// kBatch elements per thread: the running prefix products are parked in `out` itself (coalesced, re-read on the way
+// back), the domain point advances by one multiplication per element, and the a^(M-2) exponentiation (≈ 250
+// products) is amortised over kBatch = 64 elements: ≈ 11 products per element.
+__global__ void __launch_bounds__(128) pair_inverse_kernel(const uint4* __restrict__ roots, const uint4* __restrict__ roots_inv,
+                                                           uint32_t log_L, RowShard sh, fe a, fe b, uint4* __restrict__ out) {
     const uint64_t L = (1ull << log_L) >> sh.world_log;  // rows of this rank, packed index
-    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;  // a multiple of 8, so global rows advance uniformly
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    fe pre[kBatch];
+    const uint64_t gstep = nthreads << sh.world_log;             // global_row(u + nthreads) - global_row(u)
+    const fe step = fe_root_pow(roots, log_L, gstep), step_inv = fe_root_pow(roots_inv, log_L, gstep);
+    fe x = domain_point(roots, log_L, sh.global_row(t));
     fe acc = fe_one();
-#pragma unroll
     for (int q = 0; q < kBatch; q++) {
-        uint64_t i = t + q * nthreads;
-        fe d = fe_one();
-        if (i < L) {
-            fe x = domain_point(roots, log_L, sh.global_row(i));
-            d = fe_mul(fe_sub(x, a), fe_sub(x, b));
+        const uint64_t u = t + q * nthreads;
+        if (u < L) {
+            fe_store(out + u, acc);
+            acc = fe_mul(acc, fe_mul(fe_sub(x, a), fe_sub(x, b)));
         }
-        pre[q] = acc;
-        acc = fe_mul(acc, d);
+        x = fe_mul(x, step);
     }
     acc = fe_inv(acc);
-#pragma unroll
     for (int q = kBatch - 1; q >= 0; q--) {
-        uint64_t i = t + q * nthreads;
-        if (i < L) {
-            // recompute d_i instead of keeping a second register array
-            fe x = domain_point(roots, log_L, sh.global_row(i));
-            fe d = fe_mul(fe_sub(x, a), fe_sub(x, b));
-            fe_store(out + i, fe_mul(acc, pre[q]));
-            acc = fe_mul(acc, d);
+        const uint64_t u = t + q * nthreads;
+        x = fe_mul(x, step_inv);
+        if (u < L) {
+            const fe pre = fe_load(out + u);
+            fe_store(out + u, fe_mul(acc, pre));
+            acc = fe_mul(acc, fe_mul(fe_sub(x, a), fe_sub(x, b)));
         }
     }
 }
@@ -159,15 +160,15 @@ __global__ void frames_kernel(const uint4* cur, const uint4* nxt, const uint4* p
 
 }  // namespace
 
-int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, uint32_t log_L, const uint64_t a[2], const uint64_t b[2],
-                        uint4* out, RowShard sh) {
+int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, const uint4* root_inv, uint32_t log_L, const uint64_t a[2],
+                        const uint64_t b[2], uint4* out, RowShard sh) {
     const uint64_t L = (1ull << log_L) >> sh.world_log;
     const unsigned threads = 128;
     uint64_t need = (L + kBatch - 1) / kBatch;
     unsigned blocks = (unsigned)((need + threads - 1) / threads);
     {
         LaunchScope ls(s, K_PAIR_INVERSE, L * 16);
-        pair_inverse_kernel<<<blocks, threads, 0, s>>>(root_fwd, log_L, sh, fe_make(a[0], a[1]), fe_make(b[0], b[1]), out);
+        pair_inverse_kernel<<<blocks, threads, 0, s>>>(root_fwd, root_inv, log_L, sh, fe_make(a[0], a[1]), fe_make(b[0], b[1]), out);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

@@ -23,8 +23,8 @@ struct ConstraintParams {  // device-resident, rebuilt for every proof (depends 
 
 // out[i] = 1 / ((x_i - a)(x_i - b)),  x_i = 3 * w_L^i,  i < L = 2^log_L
 // (multi-GPU: out[t] for the packed rows t of this rank, x taken at global_row(t))
-int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, uint32_t log_L, const uint64_t a[2], const uint64_t b[2],
-                        uint4* out, RowShard sh = RowShard());
+int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, const uint4* root_inv, uint32_t log_L, const uint64_t a[2],
+                        const uint64_t b[2], uint4* out, RowShard sh = RowShard());
 
 // combined[i] = T_i / z_t(x_i) + B0_i / (x_i - 1) + B1_i / (x_i - g^(n-2))   
 // lde: column-major 28 x L; inv_den[i] = 1/((x_i - 1)(x_i - g^(n-2)))

@@ -96,6 +96,17 @@ __global__ void all_zero_kernel(const uint4* __restrict__ v, uint64_t count, uin
     if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
+// flag |= 2 when an element is not a canonical field element (>= M = 2^128 - 45*2^40 + 1)
+__global__ void canonical_kernel(const uint4* __restrict__ v, uint64_t count, uint32_t* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bad = 0;
+    for (; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 x = __ldg(v + i);
+        bad |= (x.w == 0xFFFFFFFFu) && (x.z == 0xFFFFFFFFu) && (x.y > 0xFFFFD300u || (x.y == 0xFFFFD300u && x.x >= 1u));
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 2u);
+}
+
 }  // namespace
 
 int eval_polys(cudaStream_t s, const uint4* coeff, uint64_t pitch, uint32_t ncols, uint32_t log_n, const uint64_t y[2][2],
@@ -134,6 +145,17 @@ int deep_pointwise(cudaStream_t s, const uint4* root_fwd, const uint4* pq_lde, u
     {
         LaunchScope ls(s, K_DEEP_POINTWISE, L * 16 * 4);
         deep_pointwise_kernel<<<(unsigned)((L + 255) / 256), 256, 0, s>>>(root_fwd, pq_lde, log_L, inv_den, sc, sh, deep);
+    }
+    EZK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+int check_canonical(cudaStream_t s, const uint4* v, uint64_t count, uint32_t* flag) {
+    unsigned blocks = (unsigned)((count + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    {
+        LaunchScope ls(s, K_ALL_ZERO, count * 16);
+        canonical_kernel<<<blocks, 256, 0, s>>>(v, count, flag);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

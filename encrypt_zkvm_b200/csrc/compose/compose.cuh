@@ -29,6 +29,9 @@ struct DeepScalars {
 int deep_pointwise(cudaStream_t s, const uint4* root_fwd, const uint4* pq_lde, uint32_t log_L, const uint4* inv_den,
                    DeepScalars sc, uint4* deep, RowShard sh = RowShard());  // multi-GPU: packed rows of this rank
 
+// *flag |= 2 when any of the `count` elements is >= M (the kernels assume canonical input, like BaseElement's memory)
+int check_canonical(cudaStream_t s, const uint4* v, uint64_t count, uint32_t* flag);
+
 // *flag |= 1 when any of the `count` elements is non-zero
 int check_all_zero(cudaStream_t s, const uint4* v, uint64_t count, uint32_t* flag);
 

@@ -128,6 +128,8 @@ GpuProver::GpuProver(int device) : device_(device) {
     for (auto& e : ev_) EZK_CUDA(cudaEventCreate(&e));
     for (auto& e : timer_ev_) EZK_CUDA(cudaEventCreate(&e));
     EZK_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    EZK_CUDA(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
+    for (auto& e : aux_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : copy_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
@@ -156,6 +158,8 @@ GpuProver::~GpuProver() {
     for (auto& e : timer_ev_) cudaEventDestroy(e);
     for (auto& e : copy_ev_) cudaEventDestroy(e);
     cudaStreamDestroy(copy_stream_);
+    for (auto& e : aux_ev_) cudaEventDestroy(e);
+    cudaStreamDestroy(aux_stream_);
     cudaFree(d_flag_);
     cudaFree(d_params_);
     cudaFreeHost(pinned_);
@@ -289,6 +293,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
 
     // ---- (1) trace upload, interpolation, LDE, commitment ----
     mark();
+    EZK_CUDA(cudaMemsetAsync(d_flag_, 0, sizeof(uint32_t), stream_));
     {
         NttScale sc{};
         put(sc.cvec[0], inverse(Fp::from_u64(n)));
@@ -309,16 +314,29 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
                 EZK_CUDA(cudaStreamWaitEvent(stream_, copy_ev_[g], 0));
                 if (g == 0) mark();
                 const size_t c0 = (size_t)g * kGroup;
+                check_canonical(stream_, d_trace_in + c0 * n, kGroup * n, d_flag_);
                 ntt_columns(tables_, stream_, d_trace_in + c0 * n, n, d_tcoef + c0 * n, n, d_tmp, kGroup, log_n, true, &sc);
                 lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L, L, d_tmp, kGroup, log_n, cs);
             }
         } else {
             mark();
+            check_canonical(stream_, device_trace, kWidth * n, d_flag_);
             ntt_columns(tables_, stream_, device_trace, n, d_tcoef, n, d_tmp, kWidth, log_n, true, &sc);
             lde_columns(tables_, stream_, d_tcoef, n, d_tlde, L, d_tmp, kWidth, log_n, cs);
         }
     }
     mark();
+    // the divisor inverses of the boundary constraints depend on n only: compute them on the auxiliary stream while
+    // the (latency-bound) Merkle tree of the trace commitment is built and its root travels to the host
+    const Fp g_last = pow(g, n - 2), g_last2 = pow(g, n - 1);
+    {
+        EZK_CUDA(cudaEventRecord(aux_ev_[0], stream_));
+        EZK_CUDA(cudaStreamWaitEvent(aux_stream_, aux_ev_[0], 0));
+        uint64_t a[2], b[2];
+        put(a, Fp(1)), put(b, g_last);
+        domain_pair_inverse(aux_stream_, tables_.root_fwd, tables_.root_inv, log_L, a, b, d_invden, sh);
+        EZK_CUDA(cudaEventRecord(aux_ev_[1], aux_stream_));
+    }
     commit_rows(d_tlde, kWidth, d_tnodes);
     last_.trace_root = root_of(d_tnodes);
     commitments.insert(commitments.end(), last_.trace_root.begin(), last_.trace_root.end());
@@ -326,7 +344,6 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     mark();
 
     // ---- (2) constraint evaluation ----
-    const Fp g_last = pow(g, n - 2), g_last2 = pow(g, n - 1);
     {
         ConstraintParams hp{};
         for (uint32_t j = 0; j < kTransitions; j++) put(hp.tcoef[j], coin.draw());
@@ -374,9 +391,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
             wr = wr * w128;
         }
         h2d(d_params_, &hp, sizeof(hp));
-        uint64_t a[2], b[2];
-        put(a, Fp(1)), put(b, g_last);
-        domain_pair_inverse(stream_, tables_.root_fwd, log_L, a, b, d_invden, sh);
+        EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[1], 0));
         evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_invden, sharded ? d_pack : d_combined, sh);
         if (sharded) share_rows(1, d_combined);
     }
@@ -393,10 +408,11 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         }
         sc.chunk_shift = log_n, sc.use_offset = 0;
         ntt_columns(tables_, stream_, d_combined, L, d_ccoef, L, d_tmp, 1, log_L, true, &sc);
-        EZK_CUDA(cudaMemsetAsync(d_flag_, 0, sizeof(uint32_t), stream_));
         check_all_zero(stream_, d_ccoef + 7 * n, n, d_flag_);
         uint32_t flag = 0;
         d2h(&flag, d_flag_, sizeof(flag));
+        if (flag & 2)
+            throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "the trace contains non-canonical field elements (values >= the modulus)"};
         if (flag)
             throw ProveFailure{EZK_ERR_CONSTRAINT_DEGREE,
                                "constraint composition polynomial has degree >= 7n: the trace does not satisfy the AIR"};
@@ -415,6 +431,16 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         uint64_t y[2][2];
         put(y[0], z * o_inv), put(y[1], zg * o_inv);
         uint4* d_ood = d_small;  // 56 + 7 elements
+        {
+            // 1 / ((x - z)(x - zg)) needs z only: auxiliary stream, overlapped with the OOD evaluation, its trip to
+            // the host and the coefficient-space combination
+            EZK_CUDA(cudaEventRecord(aux_ev_[2], stream_));  // d_invden is free once the constraint kernel is done
+            EZK_CUDA(cudaStreamWaitEvent(aux_stream_, aux_ev_[2], 0));
+            uint64_t a[2], b[2];
+            put(a, z), put(b, zg);
+            domain_pair_inverse(aux_stream_, tables_.root_fwd, tables_.root_inv, log_L, a, b, d_invden, sh);
+            EZK_CUDA(cudaEventRecord(aux_ev_[3], aux_stream_));
+        }
         eval_polys(stream_, d_tcoef, n, kWidth, log_n, y, 2, d_scratch, d_ood);
         eval_polys(stream_, d_ccoef, n, kCompCols, log_n, y, 1, d_scratch + (size_t)2 * kWidth * eval_blocks, d_ood + 2 * kWidth);
         std::vector<Fp> host(2 * kWidth + kCompCols);
@@ -438,9 +464,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         h2d(d_dc, dc.data(), dc.size() * 16);
         deep_combine_coeffs(stream_, d_tcoef, n, d_ccoef, n, log_n, d_dc, d_pq);
         lde_columns(tables_, stream_, d_pq, n, d_pqlde, L, d_tmp, 2, log_n, cs);
-        uint64_t a[2], b[2];
-        put(a, z), put(b, zg);
-        domain_pair_inverse(stream_, tables_.root_fwd, log_L, a, b, d_invden, sh);
+        EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[3], 0));
         DeepScalars ds;
         put(ds.z, z), put(ds.zg, zg), put(ds.s1, s1), put(ds.s2, s2);
         deep_pointwise(stream_, tables_.root_fwd, d_pqlde, log_L, d_invden, ds, sharded ? d_pack : d_deep, sh);

@@ -196,3 +196,39 @@ def test_air_frames_on_gpu_match_oracle(prover, oracle):
         for k in range(len(cur)):
             want = oracle.evaluate_transition(cur[k], nxt[k], per[k], delta=delta)
             assert _oracle.from_arr(got[k]) == want, f"frame {k}"
+
+
+def test_non_canonical_trace_elements_are_rejected(gpu_prover_factory):
+    """`BaseElement` memory is always canonical (< M); bytes that are not must fail loudly, not prove garbage."""
+    ezk = gpu_prover_factory
+    case = synthetic(1, 8)
+    bad = case.trace.copy()
+    bad[3, 17] = (np.uint64(0xFFFFD30000000001), np.uint64(0xFFFFFFFFFFFFFFFF))  # = M
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        with pytest.raises(ezk.ProverError) as ei:
+            p.prove(bad)
+        assert ei.value.code == -1 and "non-canonical" in ei.value.message
+        assert p.prove(case.trace).to_bytes()  # the prover stays usable
+
+
+def test_trace_shape_errors(gpu_prover_factory):
+    """Edge shapes: too short, wrong width (the AIR fixes 28 columns), zero rows."""
+    import ctypes as C
+    from encrypt_zkvm_b200 import _lib
+    ezk = gpu_prover_factory
+    case = synthetic(1, 7)
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        with pytest.raises(ezk.ProverError):
+            p.prove(case.trace[:, :32])  # n = 32 < 64
+        with pytest.raises(ezk.ProverError):
+            p.prove(case.trace[:, :0])
+        with pytest.raises(ValueError):
+            p.prove(case.trace[:27])
+        # wrong width through the raw C ABI
+        a = np.ascontiguousarray(case.trace[:27])
+        cols = (C.c_void_p * 27)(*[a[c].ctypes.data for c in range(27)])
+        t = _lib.EzkTrace(C.cast(cols, C.POINTER(C.c_void_p)), 27, a.shape[1])
+        out, out_len = C.c_void_p(), C.c_size_t()
+        rc = _lib.lib.ezk_prover_prove(p._handle, C.byref(t), C.byref(p.pub_inputs.to_c()), C.byref(p.options.to_c()),
+                                       C.byref(out), C.byref(out_len))
+        assert rc == _lib.EZK_ERR_INVALID_ARGUMENT
