@@ -232,3 +232,20 @@ def test_trace_shape_errors(gpu_prover_factory):
         rc = _lib.lib.ezk_prover_prove(p._handle, C.byref(t), C.byref(p.pub_inputs.to_c()), C.byref(p.options.to_c()),
                                        C.byref(out), C.byref(out_len))
         assert rc == _lib.EZK_ERR_INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("log_n", [6, 10, 13])
+def test_transforms_on_values_near_the_modulus(prover, oracle, log_n):
+    """Elements whose top limb is all ones (M - 1 - k: small negatives) take the kernels' rare-tail path
+    (flagged arithmetic -> exact recomputation of the butterfly group); results must still be bit-exact."""
+    rng = np.random.default_rng(900 + log_n)
+    n = 1 << log_n
+    vals = [M - 1 - int(k) for k in rng.integers(0, 1 << 40, size=n)]
+    vals[0], vals[1], vals[2] = M - 1, 0, 1
+    col = _oracle.to_arr(vals).reshape(1, n, 2)
+    for inverse in (False, True):
+        got = prover.stage_ntt(col, inverse)
+        want = oracle.interpolate(col[0]) if inverse else oracle.forward_ntt(col[0])
+        assert np.array_equal(got[0], want), inverse
+    _, want_lde = oracle.lde_column(col[0])
+    assert np.array_equal(prover.stage_lde(col)[0], want_lde)
