@@ -20,6 +20,7 @@ EZK_ERR_NO_DEVICE = -5
 EZK_ERR_CUDA = -6
 EZK_ERR_VM = -7
 EZK_ERR_INTERNAL = -8
+EZK_ERR_VERIFICATION = -9
 
 STAGES = ["upload", "trace_lde", "trace_commit", "constraints", "composition", "deep", "fri", "queries"]
 ARTIFACTS = ["trace_root", "constraint_root", "combined", "ood_trace", "ood_constraints", "deep_evals", "fri_roots",
@@ -58,6 +59,7 @@ SIGNATURES = {
                                           C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "ezk_prove": (C.c_int, [C.POINTER(EzkTrace), C.POINTER(EzkPublicInputs), C.POINTER(EzkOptions), C.POINTER(_P),
                             C.POINTER(C.c_size_t)]),
+    "ezk_prover_verify": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(EzkPublicInputs), C.c_uint32]),
     "ezk_comm_unique_id": (C.c_int, [_P]),
     "ezk_prover_join": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "ezk_prover_stage_times": (C.c_int, [_P, C.POINTER(C.c_float)]),

@@ -25,6 +25,7 @@ ORACLE_LIB = ORACLE_DIR / "liborc.so"
 SOURCES = [
     "capi.cu",
     "prover.cu",
+    "verifier.cu",
     "ntt/ntt.cu",
     "merkle/merkle.cu",
     "air/constraints.cu",

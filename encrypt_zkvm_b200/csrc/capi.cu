@@ -132,6 +132,15 @@ int ezk_prover_prove_device(ezk_prover* p, const void* d_trace, uint64_t length,
     });
 }
 
+int ezk_prover_verify(ezk_prover* p, const uint8_t* proof, size_t proof_len, const ezk_public_inputs* pub,
+                      uint32_t min_conjectured_security) {
+    return guarded([&] {
+        if (!p || !proof || !pub) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->verify(proof, proof_len, to_public(pub), min_conjectured_security);
+    });
+}
+
 int ezk_prove(const ezk_trace* trace, const ezk_public_inputs* pub, const ezk_options* opt, uint8_t** proof,
               size_t* proof_len) {
     {

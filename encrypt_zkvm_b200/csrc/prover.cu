@@ -6,6 +6,7 @@
 #include "common.h"
 #include "compose/compose.cuh"
 #include "fri/fri.cuh"
+#include "host/air_host.h"
 #include "merkle/merkle.cuh"
 #include <algorithm>
 #include <atomic>
@@ -22,33 +23,6 @@ constexpr uint32_t kWidth = 28, kCompCols = 7, kTransitions = 20, kAssertions = 
 inline void put(uint64_t dst[2], Fp v) {
     dst[0] = (uint64_t)v.v;
     dst[1] = (uint64_t)(v.v >> 64);
-}
-
-struct Pair64 {
-    uint64_t lo, hi;
-};
-const Pair64 kInvMds[16] = {EZK_RESCUE_INV_MDS_INIT};
-const Pair64 kArk[128] = {EZK_RESCUE_ARK_INIT};
-
-// interpolate 16 values over <w_16> (naive inverse DFT; 9 columns x 256 products per proof)
-std::vector<Fp> interpolate16(const Fp* values) {
-    const Fp winv = inverse(root_of_unity(4)), ninv = inverse(Fp::from_u64(16));
-    std::vector<Fp> coeffs(16);
-    for (int k = 0; k < 16; k++) {
-        Fp acc, wk = pow(winv, k), p(1);
-        for (int i = 0; i < 16; i++) {
-            acc = acc + values[i] * p;
-            p = p * wk;
-        }
-        coeffs[k] = acc * ninv;
-    }
-    return coeffs;
-}
-
-Fp horner(const std::vector<Fp>& p, Fp x) {
-    Fp acc;
-    for (size_t i = p.size(); i-- > 0;) acc = acc * x + p[i];
-    return acc;
 }
 
 }  // namespace
@@ -372,17 +346,10 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
             w8c = w8c * w8;
         }
         put(hp.g_last, g_last), put(hp.g_last2, g_last2);
-        for (int i = 0; i < 16; i++) put(hp.inv_mds[i], Fp(((u128)kInvMds[i].hi << 64) | kInvMds[i].lo));
+        for (int i = 0; i < 16; i++) put(hp.inv_mds[i], rescue_const(rescue_inv_mds()[i]));
         // periodic columns: mask + 8 ARK columns (air/src/lib.rs:201-225, rescue.rs:120-134), interpolated over
         // <w_16> and tabulated at x^(n/16) for the 128 distinct values of step mod 128
-        std::vector<std::vector<Fp>> polys;
-        for (uint32_t p = 0; p < kPeriodic; p++) {
-            Fp vals[16];
-            for (uint32_t i = 0; i < kCycle; i++)
-                vals[i] = p == 0 ? Fp::from_u64(i < 14 ? 1 : 0)
-                                 : Fp(((u128)kArk[i * 8 + (p - 1)].hi << 64) | kArk[i * 8 + (p - 1)].lo);
-            polys.push_back(interpolate16(vals));
-        }
+        const std::vector<std::vector<Fp>> polys = periodic_polys();
         const Fp on16 = pow(o, n / kCycle), w128 = root_of_unity(7);
         Fp wr(1);
         for (uint32_t r = 0; r < 128; r++) {
@@ -740,7 +707,7 @@ void GpuProver::stage_eval_frames(const void* cur, const void* nxt, const void* 
     EZK_CUDA(cudaMemcpyAsync(d_p, periodic, (size_t)nframes * 9 * 16, cudaMemcpyHostToDevice, stream_));
     ConstraintParams hp{};
     hp.delta = delta;
-    for (int i = 0; i < 16; i++) put(hp.inv_mds[i], Fp(((u128)kInvMds[i].hi << 64) | kInvMds[i].lo));
+    for (int i = 0; i < 16; i++) put(hp.inv_mds[i], rescue_const(rescue_inv_mds()[i]));
     EZK_CUDA(cudaMemcpyAsync(d_params_, &hp, sizeof(hp), cudaMemcpyHostToDevice, stream_));
     evaluate_frames(stream_, d_c, d_n, d_p, nframes, d_params_, d_o);
     EZK_CUDA(cudaMemcpyAsync(out20, d_o, (size_t)nframes * 20 * 16, cudaMemcpyDeviceToHost, stream_));

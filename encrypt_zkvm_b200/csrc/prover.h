@@ -36,6 +36,9 @@ public:
     void join(int rank, int world, const uint8_t unique_id[128]);
     int world() const { return comm_.world(); }
 
+    // winterfell::verify for this AIR (vm/src/lib.rs:91-98); throws ProveFailure{EZK_ERR_VERIFICATION} on rejection
+    void verify(const uint8_t* proof, size_t proof_len, const PublicInputs& pub, uint32_t min_conjectured_security);
+
     const float* stage_ms() const { return stage_ms_; }
     void timer_start();
     float timer_stop();

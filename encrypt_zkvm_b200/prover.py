@@ -117,6 +117,10 @@ class Proof:
         return len(self._data)
 
 
+class VerifierError(EzkError):
+    """Mirrors winterfell::VerifierError: the proof was rejected."""
+
+
 class ProverError(EzkError):
     """Mirrors winterfell::ProverError (the reference unwraps it at vm/src/lib.rs:26)."""
 
@@ -182,6 +186,17 @@ class ExecutionProver:
         rc = lib.ezk_prover_prove_device(self._handle, C.c_void_p(device_ptr), n, C.byref(pi), C.byref(opt),
                                          C.byref(out), C.byref(out_len))
         return self._finish(rc, out, out_len)
+
+    # -- verify -----------------------------------------------------------------------------------------
+    def verify(self, proof, min_conjectured_security: int = 95) -> None:
+        """`winterfell::verify(proof, pub_inputs, &MinConjecturedSecurity(95))` (vm/src/lib.rs:91-98) against this
+        prover's public inputs; raises VerifierError when the proof is rejected."""
+        data = proof.to_bytes() if isinstance(proof, Proof) else bytes(proof)
+        pi = self.pub_inputs.to_c()
+        rc = lib.ezk_prover_verify(self._handle, data, len(data), C.byref(pi), min_conjectured_security)
+        if rc == _lib.EZK_ERR_VERIFICATION:
+            raise VerifierError(rc, lib.ezk_last_error().decode())
+        check(rc)
 
     # -- multi-GPU single proof -------------------------------------------------------------------------
     def join_group(self) -> int:
@@ -271,6 +286,14 @@ class ExecutionProver:
         a = C.c_float()
         check(lib.ezk_bench_fri(self._handle, n, iters, C.byref(a)))
         return a.value
+
+
+def verify(proof, pub_inputs: PublicInputs, min_conjectured_security: int = 95, device: int = 0) -> None:
+    """`winterfell::verify::<ProcessorAir, Blake3, DefaultRandomCoin<Blake3>>(proof, pub_inputs,
+    &AcceptableOptions::MinConjecturedSecurity(95))` - vm/src/lib.rs:91-98, examples/linear_regression/src/main.rs:81-85."""
+    with ExecutionProver(ProofOptions(), pub_inputs.program_hash, pub_inputs.stack_outputs, pub_inputs.server_key,
+                         device=device) as p:
+        p.verify(proof, min_conjectured_security)
 
 
 def profile_enable(on: bool) -> None:

@@ -32,7 +32,8 @@ enum ezk_status {
     EZK_ERR_NO_DEVICE = -5,
     EZK_ERR_CUDA = -6,
     EZK_ERR_VM = -7,                          /* ProgramError / ProcessorError (message mirrors the reference's Display) */
-    EZK_ERR_INTERNAL = -8
+    EZK_ERR_INTERNAL = -8,
+    EZK_ERR_VERIFICATION = -9                 /* VerifierError: the proof was rejected (ezk_last_error() says why) */
 };
 
 /* winterfell::ProofOptions::new(32, 8, 0, FieldExtension::None, 8, 127) - vm/src/lib.rs:20 */
@@ -86,6 +87,14 @@ int ezk_prover_prove_device(ezk_prover* p, const void* d_trace, uint64_t length,
 /* One-shot convenience with a lazily created default prover on device 0 (what a Rust shim calls). */
 int ezk_prove(const ezk_trace* trace, const ezk_public_inputs* pub, const ezk_options* opt, uint8_t** proof,
               size_t* proof_len);
+
+/* winterfell::verify::<ProcessorAir, Blake3_256, DefaultRandomCoin<Blake3_256>>(proof, pub_inputs,
+ * &AcceptableOptions::MinConjecturedSecurity(min_conjectured_security)) as called at vm/src/lib.rs:91-98 and
+ * examples/linear_regression/src/main.rs:81-85.  Returns EZK_OK when the proof is accepted and
+ * EZK_ERR_VERIFICATION when it is rejected.  Transcript / Merkle / FRI checks run on the host; the AIR's
+ * transition constraints at the out-of-domain point run on the GPU (same code as the prover). */
+int ezk_prover_verify(ezk_prover* p, const uint8_t* proof, size_t proof_len, const ezk_public_inputs* pub,
+                      uint32_t min_conjectured_security);
 
 /* ---- one proof sharded over the GPUs of a box (no reference counterpart: the reference is one thread) ----
  * One process per GPU.  Rank 0 calls ezk_comm_unique_id and hands the 128 bytes to the other ranks (any

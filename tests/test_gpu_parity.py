@@ -249,3 +249,63 @@ def test_transforms_on_values_near_the_modulus(prover, oracle, log_n):
         assert np.array_equal(got[0], want), inverse
     _, want_lde = oracle.lde_column(col[0])
     assert np.array_equal(prover.stage_lde(col)[0], want_lde)
+
+
+@pytest.mark.parametrize("case_fn", [lr_case, small_case, lambda: synthetic(3, 10), lambda: synthetic(2, 13)])
+def test_product_verifier_accepts_and_agrees_with_the_oracle(gpu_prover_factory, oracle, case_fn):
+    """`ezk_prover_verify` (winterfell::verify for this AIR, vm/src/lib.rs:91-98): accepts the prover's and the
+    oracle's proofs, and returns the same accept / reject decision as the oracle verifier on every mutation."""
+    ezk = gpu_prover_factory
+    case = case_fn()
+    pub = pub_elements(case.program_hash, case.outputs)
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        proof = p.prove(case.trace).to_bytes()
+        p.verify(proof)
+        p.verify(oracle.prove(case.trace, pub).proof)
+        rng = np.random.default_rng(len(proof))
+        offsets = [0, 2, 5, 22, 25, 28, 30, 40, len(proof) - 1, len(proof) - 9] + [int(v) for v in rng.integers(0, len(proof), size=60)]
+        for off in offsets:
+            bad = bytearray(proof)
+            bad[off] ^= 1 << int(rng.integers(0, 8))
+            want_ok = oracle.verify(bytes(bad), pub) == 0
+            try:
+                p.verify(bytes(bad))
+                got_ok = True
+            except ezk.VerifierError:
+                got_ok = False
+            assert got_ok == want_ok, off
+            assert not got_ok or bytes(bad) == proof
+        with pytest.raises(ezk.VerifierError):
+            p.verify(proof[:-1])
+        with pytest.raises(ezk.VerifierError):
+            p.verify(proof + b"\x00")
+        with pytest.raises(ezk.VerifierError) as ei:
+            p.verify(proof, min_conjectured_security=96)  # 32 queries * 3 bits - 1 = 95
+        assert "security" in ei.value.message
+    wrong_out = list(case.outputs)
+    wrong_out[0] = (wrong_out[0] + 1) % M
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, wrong_out, ezk.ServerKey()) as p:
+        with pytest.raises(ezk.VerifierError):
+            p.verify(proof)
+    wrong_hash = [(case.program_hash[0] + 1) % M, case.program_hash[1]]
+    with ezk.ExecutionProver(ezk.ProofOptions(), wrong_hash, case.outputs, ezk.ServerKey()) as p:
+        with pytest.raises(ezk.VerifierError):
+            p.verify(proof)
+
+
+def test_product_verifier_on_a_2p18_proof_and_other_options(gpu_prover_factory):
+    ezk = gpu_prover_factory
+    case = synthetic(2, 18)
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        p.verify(p.prove(case.trace))
+    case = synthetic(3, 10, delta=32)
+    opt = ezk.ProofOptions(num_queries=20, grinding_factor=8, fri_remainder_max_degree=31)
+    params = ezk.LweParameters(plaintext_modulus=8, ciphertext_modulus=8 * 32)
+    with ezk.ExecutionProver(opt, case.program_hash, case.outputs, ezk.ServerKey(params)) as p:
+        proof = p.prove(case.trace)
+        p.verify(proof, min_conjectured_security=67)
+        with pytest.raises(ezk.VerifierError):
+            p.verify(proof)  # 67 bits < 95
+    with ezk.ExecutionProver(opt, case.program_hash, case.outputs, ezk.ServerKey()) as p:  # delta 16: wrong AIR parameter
+        with pytest.raises(ezk.VerifierError):
+            p.verify(proof, min_conjectured_security=67)
