@@ -349,14 +349,20 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         for (int i = 0; i < 16; i++) put(hp.inv_mds[i], rescue_const(rescue_inv_mds()[i]));
         // periodic columns: mask + 8 ARK columns (air/src/lib.rs:201-225, rescue.rs:120-134), interpolated over
         // <w_16> and tabulated at x^(n/16) for the 128 distinct values of step mod 128
-        const std::vector<std::vector<Fp>> polys = periodic_polys();
-        const Fp on16 = pow(o, n / kCycle), w128 = root_of_unity(7);
-        Fp wr(1);
-        for (uint32_t r = 0; r < 128; r++) {
-            const Fp y = on16 * wr;
-            for (uint32_t p = 0; p < kPeriodic; p++) put(hp.ptable[r * kPeriodic + p], horner(polys[p], y));
-            wr = wr * w128;
+        // (depends on n only: cached per trace length, 1152 Horner evaluations otherwise)
+        if (ptable_log_n_ != log_n) {
+            const std::vector<std::vector<Fp>> polys = periodic_polys();
+            const Fp on16 = pow(o, n / kCycle), w128 = root_of_unity(7);
+            Fp wr(1);
+            ptable_.assign(128 * kPeriodic, Fp());
+            for (uint32_t r = 0; r < 128; r++) {
+                const Fp y = on16 * wr;
+                for (uint32_t p = 0; p < kPeriodic; p++) ptable_[r * kPeriodic + p] = horner(polys[p], y);
+                wr = wr * w128;
+            }
+            ptable_log_n_ = log_n;
         }
+        for (uint32_t k = 0; k < 128 * kPeriodic; k++) put(hp.ptable[k], ptable_[k]);
         h2d(d_params_, &hp, sizeof(hp));
         EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[1], 0));
         evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_invden, sharded ? d_pack : d_combined, sh);
@@ -476,9 +482,14 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         }
         // remainder: interpolate the last layer over the coset; only the first s/8 coefficients may be non-zero
         uint4* d_rem = alloc(s);
-        uint64_t inv_s[2];
-        put(inv_s, inverse(Fp::from_u64(s)));
-        fri_remainder(stream_, tables_.root_inv, tables_.off_inv, cur, ilog2_u64(s), inv_s, d_rem);
+        {
+            // interpolation over the coset 3 * <w_s>: inverse transform, then coefficient k times 3^-k / s (the batched
+            // NTT kernels; the layer is at most 4096 points)
+            NttScale sc{};
+            put(sc.cvec[0], inverse(Fp::from_u64(s)));
+            sc.chunk_shift = 63, sc.use_offset = 2;
+            ntt_columns(tables_, stream_, cur, s, d_rem, s, d_tmp, 1, ilog2_u64(s), true, &sc);
+        }
         std::vector<Fp> all(s);
         d2h(all.data(), d_rem, s * 16);
         for (uint64_t i = s / 8; i < s; i++)
@@ -512,41 +523,75 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     w.u16((uint16_t)commitments.size());
     w.bytes(commitments.data(), commitments.size());
 
+    // All openings (trace rows, constraint rows, one per FRI layer) are planned on the host first, fetched with ONE
+    // index upload, a burst of gather kernels and ONE read-back, and serialized afterwards.
     uint64_t* d_idx = reinterpret_cast<uint64_t*>(alloc(8192));  // up to 16384 u64 indices
     uint4* d_gather = alloc(32768);
-    // rows at `pos` from a column-major table + batch Merkle proof over `nodes`
-    // `rows_sharded`: the table holds only this rank's LDE rows (multi-GPU), so every opened row is taken from
-    // the all-gathered copy of its owner; the Merkle nodes are replicated on every rank.
-    auto write_opening = [&](const uint4* table, uint64_t pitch, uint32_t width, const uint4* nodes, uint64_t num_leaves,
-                             const std::vector<uint64_t>& pos, bool rows_sharded) {
-        const uint32_t nq = (uint32_t)pos.size();
-        auto idx_lists = batch_proof_node_indices(num_leaves, pos);
-        std::vector<uint64_t> flat(pos);
-        for (auto& v : idx_lists) flat.insert(flat.end(), v.begin(), v.end());
-        const size_t ndig = flat.size() - nq;
-        if (flat.size() > 16384 || (size_t)nq * width + 2 * ndig > 32768)
-            throw ProveFailure{EZK_ERR_INTERNAL, "query staging too small"};
-        h2d(d_idx, flat.data(), flat.size() * 8);
-        gather_rows(stream_, table, pitch, width, d_idx, nq, d_gather);
-        if (ndig) gather_digests(stream_, nodes, d_idx + nq, (uint32_t)ndig, d_gather + (size_t)nq * width);
-        std::vector<uint8_t> host((size_t)nq * width * 16 + ndig * 32);
-        d2h(host.data(), d_gather, host.size());
-        const size_t vbytes = (size_t)nq * width * 16;
-        if (rows_sharded) {
-            comm_.all_gather(d_gather, d_allg, vbytes, stream_);
-            count_launch();
-            std::vector<uint8_t> all(vbytes * comm_.world());
-            d2h(all.data(), d_allg, all.size());
-            for (uint32_t q = 0; q < nq; q++)
-                memcpy(host.data() + (size_t)q * width * 16, all.data() + sh.owner(pos[q]) * vbytes + (size_t)q * width * 16,
-                       (size_t)width * 16);
+    struct Opening {
+        const uint4* table;
+        uint64_t pitch;
+        uint32_t width;
+        const uint4* nodes;
+        uint64_t num_leaves;
+        std::vector<uint64_t> pos;
+        std::vector<std::vector<uint64_t>> idx_lists;
+        size_t idx_off, ndig, out_off;  // offsets into the index array / the gather buffer (16-byte units)
+    };
+    std::vector<Opening> ops;
+    std::vector<uint64_t> flat;
+    size_t out_units = 0;
+    auto plan_opening = [&](const uint4* table, uint64_t pitch, uint32_t width, const uint4* nodes, uint64_t num_leaves,
+                            const std::vector<uint64_t>& pos) {
+        Opening o{table, pitch, width, nodes, num_leaves, pos, batch_proof_node_indices(num_leaves, pos), flat.size(), 0, out_units};
+        flat.insert(flat.end(), pos.begin(), pos.end());
+        for (auto& v : o.idx_lists) flat.insert(flat.end(), v.begin(), v.end());
+        o.ndig = flat.size() - o.idx_off - pos.size();
+        out_units += pos.size() * width + 2 * o.ndig;
+        ops.push_back(std::move(o));
+    };
+    plan_opening(d_tlde, L, kWidth, d_tnodes, L, positions);
+    plan_opening(d_clde, L, kCompCols, d_cnodes, L, positions);
+    const size_t lde_units = out_units;  // the part that holds rows of the (possibly sharded) LDE tables
+    {
+        std::vector<uint64_t> pos = positions;
+        for (auto& layer : layers) {
+            pos = fold_positions(pos, layer.size, 8);
+            plan_opening(layer.evals, layer.size / 8, 8, layer.nodes, layer.size / 8, pos);
         }
+    }
+    if (flat.size() > 16384 || out_units > 32768 || out_units * 16 * (sharded ? comm_.world() : 1) > pinned_bytes_)
+        throw ProveFailure{EZK_ERR_INTERNAL, "query staging too small"};
+    h2d(d_idx, flat.data(), flat.size() * 8);
+    for (auto& o : ops) {
+        const uint32_t nq = (uint32_t)o.pos.size();
+        gather_rows(stream_, o.table, o.pitch, o.width, d_idx + o.idx_off, nq, d_gather + o.out_off);
+        if (o.ndig)
+            gather_digests(stream_, o.nodes, d_idx + o.idx_off + nq, (uint32_t)o.ndig, d_gather + o.out_off + (size_t)nq * o.width);
+    }
+    std::vector<uint8_t> fetched(out_units * 16);
+    d2h(fetched.data(), d_gather, fetched.size());
+    if (sharded) {
+        // the LDE tables hold only this rank's rows: take every opened row from the all-gathered copy of its owner
+        // (the Merkle nodes are replicated on every rank)
+        comm_.all_gather(d_gather, d_allg, lde_units * 16, stream_);
+        count_launch();
+        std::vector<uint8_t> all(lde_units * 16 * comm_.world());
+        d2h(all.data(), d_allg, all.size());
+        for (size_t k = 0; k < 2; k++)
+            for (size_t q = 0; q < ops[k].pos.size(); q++) {
+                const size_t off = (ops[k].out_off + q * ops[k].width) * 16;
+                memcpy(fetched.data() + off, all.data() + sh.owner(ops[k].pos[q]) * lde_units * 16 + off, (size_t)ops[k].width * 16);
+            }
+    }
+    auto write_opening = [&](const Opening& o) {
+        const size_t vbytes = o.pos.size() * o.width * 16;
+        const uint8_t* base = fetched.data() + o.out_off * 16;
         w.u32((uint32_t)vbytes);
-        w.bytes(host.data(), vbytes);
+        w.bytes(base, vbytes);
         std::vector<uint8_t> paths;
-        paths.push_back((uint8_t)idx_lists.size());
-        const uint8_t* dg = host.data() + vbytes;
-        for (auto& v : idx_lists) {
+        paths.push_back((uint8_t)o.idx_lists.size());
+        const uint8_t* dg = base + vbytes;
+        for (auto& v : o.idx_lists) {
             paths.push_back((uint8_t)v.size());
             paths.insert(paths.end(), dg, dg + v.size() * 32);
             dg += v.size() * 32;
@@ -554,8 +599,8 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         w.u32((uint32_t)paths.size());
         w.bytes(paths.data(), paths.size());
     };
-    write_opening(d_tlde, L, kWidth, d_tnodes, L, positions, sharded);
-    write_opening(d_clde, L, kCompCols, d_cnodes, L, positions, sharded);
+    write_opening(ops[0]);
+    write_opening(ops[1]);
     // OodFrame
     w.u16((uint16_t)(1 + ood_trace.size() * 16));
     w.u8(2);
@@ -565,14 +610,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     for (Fp v : ood_comp) w.element(v);
     // FriProof
     w.u8((uint8_t)nlayers);
-    {
-        std::vector<uint64_t> pos = positions;
-        for (auto& layer : layers) {
-            pos = fold_positions(pos, layer.size, 8);
-            const uint64_t m = layer.size / 8;
-            write_opening(layer.evals, m, 8, layer.nodes, m, pos, false);
-        }
-    }
+    for (size_t k = 2; k < ops.size(); k++) write_opening(ops[k]);
     w.u16((uint16_t)(remainder.size() * 16));
     for (Fp v : remainder) w.element(v);
     w.u8(1);

@@ -80,6 +80,8 @@ private:
     cudaEvent_t ev_[16];
     cudaEvent_t timer_ev_[2];
     float stage_ms_[8] = {0};
+    std::vector<Fp> ptable_;        // periodic columns over the LDE domain, cached per trace length
+    uint32_t ptable_log_n_ = 0;
 
     // state of the last proof (device pointers into the arena + host copies), for ezk_prover_artifact
     struct Last {
