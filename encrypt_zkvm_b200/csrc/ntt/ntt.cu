@@ -17,6 +17,7 @@
 #include "../field/f128.cuh"
 #include "../field/f128_host.h"
 #include "../common.h"
+#include <map>
 #include <vector>
 
 namespace ezk {
@@ -254,12 +255,14 @@ struct StridedArgs {
     uint32_t inv;
     const uint4* roots;             // two-level 2^28-th root table (forward or inverse)
     const uint4* tw;                // compact per-size tables (same direction)
+    const uint4* big;               // optional full inter-pass twiddle table (see build_pass_table), else nullptr
 };
 
 struct StridedPass {
     const uint4* src;
     uint4* dst;
     const uint4* roots;
+    const uint4* big;  // big[(coset << log_N) + (j << log_stride) + lo] = w_L^(lo (8 j + coset)) (w_N^(lo j) for plain passes)
     uint64_t base;
     uint32_t lo0, log_stride, log_N, coset, log_L;
     // LDE first pass: the coset factor w_L^(c * idx), idx = lo + stride * m, splits into w_L^(c * stride * m)
@@ -274,6 +277,7 @@ struct StridedPass {
     }
     template <class A>
     __device__ __forceinline__ fe finish(A& ar, uint32_t lane, uint32_t j, fe v) const {
+        if (big) return ar.mul(v, fe_ldg(big + ((uint64_t)coset << log_N) + ((uint64_t)j << log_stride) + lo0 + lane));
         const uint64_t ex = (uint64_t)(lo0 + lane) * (((uint64_t)j << (log_L - log_N)) + coset);
         return ex != 0 ? ar.mul(v, root_pow(ar, roots, log_L, ex)) : v;
     }
@@ -301,6 +305,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_strided_pass(StridedArgs a)
     }
     P.dst = a.dst + (uint64_t)col * a.dst_pitch;
     P.roots = a.roots;
+    P.big = a.big;
     P.log_stride = a.log_stride, P.log_N = a.log_stride + a.log_s;
     P.log_L = a.coset_first ? a.log_L : P.log_N;  // plain passes: exponent lo * j of w_N
     tile_transform(P, tile, a.log_s, a.lanes_log, a.inv, a.tw);
@@ -473,6 +478,42 @@ void launch_final(dim3 grid, size_t smem, cudaStream_t s, const FinalArgs& a) {
         ntt_final_pass<256, 3><<<grid, threads_for(a.log_s, a.lanes_log, 256), smem, s>>>(a);
 }
 
+// Full inter-pass twiddle table of one strided pass: entry (c << log_N) + (j << log_stride) + lo =
+// w_L^(lo (8 j + c)) for the LDE's first pass (c = coset, 8 N entries) or w_N^(lo j) for a plain pass (N entries).
+// It replaces the two-level lookup (2 loads + 1 product per element) by one coalesced load; the kernels are
+// integer-pipe bound, so trading a product for 16 more bytes of (L2 / HBM) traffic per element pays.
+__global__ void build_pass_table_kernel(const uint4* __restrict__ roots, uint32_t log_N, uint32_t log_stride, uint32_t log_L,
+                                        uint32_t ncosets, uint4* __restrict__ out) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ((uint64_t)ncosets << log_N)) return;
+    const uint64_t c = e >> log_N, idx = e & ((1ull << log_N) - 1);
+    const uint64_t j = idx >> log_stride, lo = idx & ((1ull << log_stride) - 1);
+    fe_store(out + e, fe_root_pow(roots, log_L, lo * ((j << (log_L - log_N)) + c)));
+}
+
+const uint4* pass_table(const NttTables& t, cudaStream_t s, bool inverse, bool coset, uint32_t log_N, uint32_t log_stride,
+                        uint32_t log_L) {
+    const uint64_t entries = (coset ? 8ull : 1ull) << log_N;
+    if (!t.big_tables || entries * 16 > t.big_table_limit_bytes) return nullptr;
+    const uint64_t key = ((uint64_t)log_N << 32) | ((uint64_t)log_stride << 16) | ((uint64_t)coset << 1) | (uint64_t)inverse;
+    auto it = t.big_tables->find(key);
+    if (it != t.big_tables->end()) return it->second;
+    uint4* d = nullptr;
+    if (cudaMalloc(&d, entries * 16) != cudaSuccess) {
+        cudaGetLastError();
+        (*t.big_tables)[key] = nullptr;  // not enough memory: keep using the two-level tables
+        return nullptr;
+    }
+    {
+        LaunchScope ls(s, K_NTT_STRIDED, entries * 16);
+        build_pass_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, s>>>(inverse ? t.root_inv : t.root_fwd, log_N, log_stride,
+                                                                                 coset ? log_L : log_N, coset ? 8 : 1, d);
+    }
+    EZK_CUDA(cudaGetLastError());
+    (*t.big_tables)[key] = d;
+    return d;
+}
+
 // strided passes p..2 over `ncols` arrays of n elements: the first pass reads `first_src` and writes `buf`,
 // later passes run in place in `buf`.  With `coset` the first pass reads coefficient column y/8 and applies the
 // coset factor w_L^(c*m), c = y%8 (LDE).
@@ -496,6 +537,7 @@ int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log
         a.inv = inverse ? 1 : 0;
         a.roots = inverse ? t.root_inv : t.root_fwd;
         a.tw = inverse ? t.tw_inv : t.tw_fwd;
+        a.big = pass_table(t, s, inverse, a.coset_first != 0, log_stride + a.log_s, log_stride, log_L);
         dim3 grid((unsigned)(((uint64_t)1 << (log_n - pl.log_d[i])) >> a.lanes_log), ncols);
         {
             // compulsory traffic: every element of every column read once and written once (the 8 coset copies of
@@ -559,6 +601,8 @@ void ntt_tables_init(NttTables& t) {
     Fp w8[2][4];
     for (int e = 0; e < 4; e++) w8[0][e] = cf[8 + e], w8[1][e] = ci[8 + e];
     EZK_CUDA(cudaMemcpyToSymbol(c_w8, w8, sizeof(w8)));
+    t.big_tables = new std::map<uint64_t, uint4*>();
+    if (const char* e = getenv("EZK_NTT_BIG_TABLE_MB")) t.big_table_limit_bytes = (uint64_t)atoll(e) << 20;
     const char* env = getenv("EZK_NTT_TILE_LOG");
     if (env) {
         int v = atoi(env);
@@ -569,6 +613,10 @@ void ntt_tables_init(NttTables& t) {
 void ntt_tables_free(NttTables& t) {
     cudaFree(t.root_fwd), cudaFree(t.root_inv), cudaFree(t.off_fwd), cudaFree(t.off_inv);
     cudaFree(t.tw_fwd), cudaFree(t.tw_inv);
+    if (t.big_tables) {
+        for (auto& kv : *t.big_tables) cudaFree(kv.second);
+        delete t.big_tables;
+    }
     t = NttTables{};
 }
 

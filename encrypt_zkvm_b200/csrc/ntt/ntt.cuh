@@ -3,6 +3,7 @@
 // DefaultTraceLde::new (prover/src/lib.rs:55-62), CompositionPoly::new and the DEEP/FRI LDEs.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <cuda_runtime.h>
 
 namespace ezk {
@@ -16,6 +17,10 @@ struct NttTables {
     // compact per-size tables: entry (1 << k) + e = w_{2^k}^e (forward) / w_{2^k}^-e (inverse), k <= 11
     uint4* tw_fwd = nullptr;
     uint4* tw_inv = nullptr;
+    // full inter-pass twiddle tables of the strided passes, built on first use per (size, direction) and kept
+    // (16 MiB for a plain 2^20 pass, 128 MiB for the 2^20 LDE); sizes above the limit use the two-level tables
+    std::map<uint64_t, uint4*>* big_tables = nullptr;
+    uint64_t big_table_limit_bytes = 1ull << 30;
     int max_tile_log = 10;      // largest single-CTA transform (2^10 points x 4 lanes, 2^9 x 8 lanes)
 };
 
