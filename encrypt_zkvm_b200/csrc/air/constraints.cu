@@ -77,12 +77,12 @@ struct SumSink {
 };
 
 // combined evaluation of one LDE row; returns true when the FAST arithmetic hit a rare tail (value unusable)
-template <bool FAST>
+template <class AR>
 __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, const uint4* __restrict__ lde, uint64_t pitch,
                                                uint32_t log_L, const ConstraintParams* __restrict__ p,
                                                const uint4* __restrict__ inv_den, uint64_t packed, uint64_t i, fe& result) {
     const uint64_t L = 1ull << log_L;
-    Arith<FAST> ar;
+    AR ar;
     LdeFrame f{lde, pitch, i, (i + 8) & (L - 1)};
     fe periodic[9];
     {
@@ -92,6 +92,7 @@ __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, 
     }
     SumSink sink{p, fe_zero()};
     eval_transition(ar, f, periodic, reinterpret_cast<const AirConsts*>(p->inv_mds), p->delta, sink);
+    ar.checkpoint();
     fe x = root_pow_policy(ar, roots, log_L, i);
     x = ar.add(ar.add(x, x), x);  // x_i = 3 * w_L^i
     const fe a = ld2(p->g_last);
@@ -102,8 +103,10 @@ __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, 
     fe s0 = fe_zero(), s1 = fe_zero();
 #pragma unroll
     for (int k = 0; k < 12; k++) s0 = ar.add(s0, ar.mul(ld2(p->bcoef[k]), f.cur(p->bcol[k])));
+    ar.checkpoint();
 #pragma unroll
     for (int k = 12; k < 22; k++) s1 = ar.add(s1, ar.mul(ld2(p->bcoef[k]), ar.sub(f.cur(p->bcol[k]), ld2(p->bval[k]))));
+    ar.checkpoint();
     // B0/(x-1) + B1/(x-a) = (B0 (x-a) + B1 (x-1)) / ((x-1)(x-a))
     const fe num = ar.add(ar.mul(s0, ar.sub(x, a)), ar.mul(s1, ar.sub(x, fe_one())));
     const fe bsum = ar.mul(num, fe_ldg(inv_den + packed));
@@ -115,11 +118,11 @@ __device__ __noinline__ fe constraint_row_exact(const uint4* __restrict__ roots,
                                                 uint32_t log_L, const ConstraintParams* __restrict__ p,
                                                 const uint4* __restrict__ inv_den, uint64_t t, uint64_t i) {
     fe r;
-    constraint_row<false>(roots, lde, pitch, log_L, p, inv_den, t, i, r);
+    constraint_row<Arith<false>>(roots, lde, pitch, log_L, p, inv_den, t, i, r);
     return r;
 }
 
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, class AR>
 __global__ void __launch_bounds__(THREADS, MINB) constraint_kernel(const uint4* __restrict__ roots, const uint4* __restrict__ lde,
                                                                    uint64_t pitch, uint32_t log_L,
                                                                    const ConstraintParams* __restrict__ p,
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, MINB) constraint_kernel(const uint4* 
     if (t >= ((1ull << log_L) >> sh.world_log)) return;
     const uint64_t i = sh.global_row(t);
     fe r;
-    if (constraint_row<true>(roots, lde, pitch, log_L, p, inv_den, t, i, r))
+    if (constraint_row<AR>(roots, lde, pitch, log_L, p, inv_den, t, i, r))
         r = constraint_row_exact(roots, lde, pitch, log_L, p, inv_den, t, i);
     fe_store(combined + t, r);
 }
@@ -180,18 +183,19 @@ int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde
     static int variant = -1;
     if (variant < 0) {
         const char* env = getenv("EZK_CONSTRAINT_VARIANT");
-        variant = env ? atoi(env) : 0;
+        variant = env ? atoi(env) : 2;  // 256-thread lockstep CTAs, 2 per SM: 5.4 ms at 2^20 against 6.25 without barriers
     }
     {
         LaunchScope ls(s, K_CONSTRAINTS, L * 16 * (28 + 2));  // 28 columns + inv_den read, 1 column written
-        if (variant == 1)
-            constraint_kernel<128, 3><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
-        else if (variant == 2)
-            constraint_kernel<128, 6><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
-        else if (variant == 3)
-            constraint_kernel<128, 8><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
+        // lockstep variants need full CTAs (every thread reaches every barrier): L is a multiple of 512 for n >= 64
+        if (variant == 1 && L % 512 == 0)
+            constraint_kernel<512, 1, ArithLockstep><<<(unsigned)(L / 512), 512, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
+        else if (variant == 2 && L % 256 == 0)
+            constraint_kernel<256, 2, ArithLockstep><<<(unsigned)(L / 256), 256, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
+        else if (variant == 3 && L % 1024 == 0)
+            constraint_kernel<1024, 1, ArithLockstep><<<(unsigned)(L / 1024), 1024, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
         else
-            constraint_kernel<128, 4><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
+            constraint_kernel<128, 4, Arith<true>><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

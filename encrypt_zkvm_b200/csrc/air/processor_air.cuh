@@ -48,6 +48,7 @@ __device__ __forceinline__ void rescue_inv_mds(A& ar, const AirConsts* __restric
             acc = ar.add(acc, ar.mul(c, v[j]));
         }
         out[i] = acc;
+        ar.checkpoint();
     }
 }
 
@@ -63,13 +64,16 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
     // left-to-right products because multiplication in the field is exact
     const fe n3n4 = ar.mul(n3, n4), b3n4 = ar.mul(b3, n4), b3b4 = ar.mul(b3, b4), n3b4 = ar.mul(n3, b4);
     const fe n0b1 = ar.mul(n0, b1);
+    ar.checkpoint();
     const fe arith = ar.mul(n0b1, n2);                    // !b0 * b1 * !b2
     const fe io = ar.mul(ar.mul(b0, n1), n2);             // b0 * !b1 * !b2
     const fe f_add = ar.mul(arith, n3n4), f_sadd = ar.mul(arith, b3n4), f_add2 = ar.mul(arith, b3b4);
     const fe f_mul = ar.mul(arith, n3b4), f_smul = ar.mul(ar.mul(n0b1, b2), n3n4);
+    ar.checkpoint();
     const fe f_push = ar.mul(io, n3n4), f_read = ar.mul(io, n3b4), f_read2 = ar.mul(io, b3n4);
     const fe f_noop = ar.mul(ar.mul(ar.mul(n0, n1), n2), n3n4);
 
+    ar.checkpoint();
     // r0: clk' - (clk + 1)                                   constrains.rs:95-97
     sink.put(ar, 0, ar.sub(f.nxt(0), ar.add(f.cur(0), one)));
     // r1: (d' - d - shr + shl) - 4*read2 + 4*add2            constrains.rs:103-106
@@ -88,6 +92,7 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
     sink.put(ar, 3, ar.mul(f_add, ar.sub(sn0, ar.add(s0, s1))));
     // r6: mul * (s0' - s0*s1)                                constrains.rs:146-148
     sink.put(ar, 6, ar.mul(f_mul, ar.sub(sn0, ar.mul(s0, s1))));
+    ar.checkpoint();
     // ciphertext ops: lwe_size = 5 (SURVEY 8b "constraints discovered")
     {
         fe acc_sadd = fe_zero(), acc_add2 = fe_zero(), acc_smul = fe_zero();
@@ -103,10 +108,12 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
             // smul: s0 * s_{1+j}                               constrains.rs:150-164, server_key.rs:116-124
             acc_smul = ar.add(acc_smul, ar.sub(snj, ar.mul(sj1, s0)));
         }
+        ar.checkpoint();
         sink.put(ar, 4, ar.mul(f_sadd, acc_sadd));
         sink.put(ar, 5, ar.mul(f_add2, acc_add2));
         sink.put(ar, 7, ar.mul(f_smul, acc_smul));
     }
+    ar.checkpoint();
     // r8..r11                                                 constrains.rs:166-180
     {
         const fe d1 = ar.sub(sn1, s0);
@@ -123,16 +130,20 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
         const fe gate_copy = ar.mul(ar.sub(one, hash_flag), h0);
         fe h[4] = {f.cur(7), f.cur(8), f.cur(9), f.cur(10)};
         fe hn[4] = {f.nxt(7), f.nxt(8), f.nxt(9), f.nxt(10)};
+        ar.checkpoint();
         // hash copy (r16..r19)
         sink.put(ar, 16, ar.mul(ar.sub(hn[0], h[0]), gate_copy));
         sink.put(ar, 17, ar.mul(ar.sub(hn[1], h[1]), gate_copy));
         sink.put(ar, 18, ar.mul(hn[2], gate_copy));
         sink.put(ar, 19, ar.mul(hn[3], gate_copy));
+        ar.checkpoint();
         // forward half: MDS * h^3 + ark[0..4], + opcode / pushed value
         fe c[4], step0[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) c[i] = ar.cube(h[i]);
+        ar.checkpoint();
         rescue_mds(ar, c, step0);
+        ar.checkpoint();
 #pragma unroll
         for (int i = 0; i < 4; i++) step0[i] = ar.add(step0[i], periodic[1 + i]);
         // opcode = 16 b0 + 8 b1 + 4 b2 + 2 b3 + b4              flags.rs:81-87
@@ -143,11 +154,13 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
         opcode = ar.add(opcode, b4);
         step0[0] = ar.add(step0[0], opcode);
         step0[1] = ar.add(step0[1], ar.mul(sn0, f_push));
+        ar.checkpoint();
         // backward half: (INV_MDS * (h' - ark[4..8]))^3
         fe d[4], step1[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) d[i] = ar.sub(hn[i], periodic[5 + i]);
         rescue_inv_mds(ar, k, d, step1);
+        ar.checkpoint();
 #pragma unroll
         for (int i = 0; i < 4; i++) sink.put(ar, 12 + i, ar.mul(ar.sub(ar.cube(step1[i]), step0[i]), gate_round));
     }

@@ -306,6 +306,14 @@ struct Arith {
     __device__ __forceinline__ fe cube(fe a) { return mul(mul(a, a), a); }
     __device__ __forceinline__ fe mul_small(fe a, uint32_t k) { return FAST ? fe_mul_small_flag(a, k, rare) : fe_mul_small(a, k); }
     __device__ __forceinline__ bool tainted() const { return FAST && rare == 0xFFFFFFFFu; }
+    __device__ __forceinline__ void checkpoint() {}
+};
+
+// Same arithmetic, but checkpoint() is a CTA barrier: in a kernel whose straight-line code is larger than the
+// instruction cache, keeping all warps of a CTA inside the same stretch of code turns per-warp instruction fetches
+// into shared ones.  Every thread of the CTA must execute the same checkpoints.
+struct ArithLockstep : Arith<true> {
+    __device__ __forceinline__ void checkpoint() { __syncthreads(); }
 };
 
 __device__ __forceinline__ fe fe_mul_small_flag(fe a, uint32_t k, uint32_t& rare) {
