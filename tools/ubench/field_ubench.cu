@@ -10,6 +10,8 @@ using namespace ezk::dev;
 template <int OP, int CHAINS>
 __global__ void __launch_bounds__(256) kern(uint4* out, int iters, uint4 seed) {
     fe x[CHAINS], w = fe_from(seed);
+    fe_pre wp;
+    wp.w[0] = w, wp.w[1] = fe_make(seed.y * 3u + 1u, seed.z), wp.w[2] = fe_make(seed.x + 7u, seed.w), wp.w[3] = fe_make(seed.z, seed.x);
     for (int c = 0; c < CHAINS; c++) x[c] = fe_make(threadIdx.x * 977u + c * 131u + 5u, blockIdx.x + 3u + c);
     uint32_t rare = 0;
     for (int it = 0; it < iters; it++) {
@@ -19,6 +21,11 @@ __global__ void __launch_bounds__(256) kern(uint4* out, int iters, uint4 seed) {
             if (OP == 1) x[c] = fe_add_flag(x[c], w, rare);
             if (OP == 2) x[c] = fe_sub(x[c], w);
             if (OP == 3) x[c] = fe_mul(x[c], w);
+            if (OP == 5) x[c] = fe_mul_pre_flag(x[c], wp, rare);  // product with a table constant in precomputed form
+            if (OP == 6) {  // NTT butterfly: add, sub, precomputed-form twiddle product
+                fe s = fe_add_flag(x[c], w, rare), d = fe_sub(x[c], w);
+                x[c] = fe_add_flag(s, fe_mul_pre_flag(d, wp, rare), rare);
+            }
             if (OP == 4) {  // butterfly-like mix: 1 mul + 1 add + 1 sub
                 fe s = fe_add_flag(x[c], w, rare), d = fe_sub(x[c], w);
                 x[c] = fe_add_flag(s, fe_mul_flag(d, w, rare), rare);
@@ -67,6 +74,9 @@ int main() {
     run<3, 8>("mul_exact", 4);
     run<1, 8>("add_flag", 4);
     run<2, 8>("sub", 4);
+    run<5, 8>("mul_pre", 4);
+    run<5, 4>("mul_pre", 4);
+    run<6, 8>("bfly_pre", 4);
     run<4, 8>("bfly", 4);
     run<4, 8>("bfly", 3);
     cudaError_t e = cudaDeviceSynchronize();
