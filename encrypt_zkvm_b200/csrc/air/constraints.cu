@@ -73,7 +73,7 @@ struct SumSink {
     const ConstraintParams* __restrict__ p;
     fe acc;
     template <class A>
-    __device__ __forceinline__ void put(A& ar, int j, fe v) { acc = ar.add(acc, ar.mul(ld2(p->tcoef[j]), v)); }
+    __device__ __forceinline__ void put(A& ar, int j, fe v) { acc = ar.add(acc, ar.mul_pre(v, ld_pre(p->tcoef_pre[j]))); }
 };
 
 // combined evaluation of one LDE row; returns true when the FAST arithmetic hit a rare tail (value unusable)
@@ -91,7 +91,7 @@ __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, 
         for (int k = 0; k < 9; k++) periodic[k] = ld2(row[k]);
     }
     SumSink sink{p, fe_zero()};
-    eval_transition(ar, f, periodic, reinterpret_cast<const AirConsts*>(p->inv_mds), p->delta, sink);
+    eval_transition(ar, f, periodic, reinterpret_cast<const AirConsts*>(p->inv_mds_pre), p->delta, sink);
     ar.checkpoint();
     fe x = root_pow_policy(ar, roots, log_L, i);
     x = ar.add(ar.add(x, x), x);  // x_i = 3 * w_L^i
@@ -102,10 +102,10 @@ __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, 
     // boundary groups: step 0 (12 assertions, all values zero) and step n-2 (10 assertions)
     fe s0 = fe_zero(), s1 = fe_zero();
 #pragma unroll
-    for (int k = 0; k < 12; k++) s0 = ar.add(s0, ar.mul(ld2(p->bcoef[k]), f.cur(p->bcol[k])));
+    for (int k = 0; k < 12; k++) s0 = ar.add(s0, ar.mul_pre(f.cur(p->bcol[k]), ld_pre(p->bcoef_pre[k])));
     ar.checkpoint();
 #pragma unroll
-    for (int k = 12; k < 22; k++) s1 = ar.add(s1, ar.mul(ld2(p->bcoef[k]), ar.sub(f.cur(p->bcol[k]), ld2(p->bval[k]))));
+    for (int k = 12; k < 22; k++) s1 = ar.add(s1, ar.mul_pre(ar.sub(f.cur(p->bcol[k]), ld2(p->bval[k])), ld_pre(p->bcoef_pre[k])));
     ar.checkpoint();
     // B0/(x-1) + B1/(x-a) = (B0 (x-a) + B1 (x-1)) / ((x-1)(x-a))
     const fe num = ar.add(ar.mul(s0, ar.sub(x, a)), ar.mul(s1, ar.sub(x, fe_one())));
@@ -158,7 +158,7 @@ __global__ void frames_kernel(const uint4* cur, const uint4* nxt, const uint4* p
     for (int k = 0; k < 9; k++) per[k] = fe_load(periodic + 9 * t + k);
     StoreSink sink{out + 20 * t};
     Arith<false> ar;
-    eval_transition(ar, f, per, reinterpret_cast<const AirConsts*>(p->inv_mds), p->delta, sink);
+    eval_transition(ar, f, per, reinterpret_cast<const AirConsts*>(p->inv_mds_pre), p->delta, sink);
 }
 
 }  // namespace

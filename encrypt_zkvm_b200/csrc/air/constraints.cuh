@@ -19,6 +19,11 @@ struct ConstraintParams {  // device-resident, rebuilt for every proof (depends 
     uint64_t g_last2[2];       // g^(n-1)
     uint64_t inv_mds[16][2];   // crypto/src/rescue.rs:216-233
     uint64_t ptable[128 * 9][2];  // periodic values, row = step mod 128
+    // the constant multipliers once more in precomputed form (c * 2^(32 i), i = 0..3: fe_pre in f128.cuh), so that the
+    // 58 products of a row that have a per-proof constant operand cost 16 IMAD.WIDE + one small fold each
+    uint64_t tcoef_pre[20][4][2];
+    uint64_t bcoef_pre[22][4][2];
+    uint64_t inv_mds_pre[16][4][2];
 };
 
 // out[i] = 1 / ((x_i - a)(x_i - b)),  x_i = 3 * w_L^i,  i < L = 2^log_L

@@ -12,8 +12,15 @@ namespace ezk {
 namespace dev {
 
 struct AirConsts {
-    uint64_t inv_mds[16][2];  // crypto/src/rescue.rs:216-233 (full-size constants)
+    uint64_t inv_mds[16][4][2];  // crypto/src/rescue.rs:216-233 (full-size constants), precomputed form (fe_pre)
 };
+
+__device__ __forceinline__ fe_pre ld_pre(const uint64_t (*c)[2]) {
+    fe_pre r;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.w[i] = fe_make(c[i][0], c[i][1]);
+    return r;
+}
 
 
 // MDS * v with the reference's matrix (crypto/src/rescue.rs:197-214). Entries are small in absolute value
@@ -44,8 +51,7 @@ __device__ __forceinline__ void rescue_inv_mds(A& ar, const AirConsts* __restric
         fe acc = fe_zero();
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            fe c = fe_make(k->inv_mds[i * 4 + j][0], k->inv_mds[i * 4 + j][1]);
-            acc = ar.add(acc, ar.mul(c, v[j]));
+            acc = ar.add(acc, ar.mul_pre(v[j], ld_pre(k->inv_mds[i * 4 + j])));
         }
         out[i] = acc;
         ar.checkpoint();

@@ -24,6 +24,14 @@ inline void put(uint64_t dst[2], Fp v) {
     dst[0] = (uint64_t)v.v;
     dst[1] = (uint64_t)(v.v >> 64);
 }
+// precomputed form of a constant multiplier: c * 2^(32 i), i = 0..3 (fe_pre in f128.cuh)
+inline void put_pre(uint64_t dst[4][2], Fp v) {
+    const Fp two32 = Fp((u128)1 << 32);
+    for (int i = 0; i < 4; i++) {
+        put(dst[i], v);
+        v = v * two32;
+    }
+}
 
 }  // namespace
 
@@ -320,19 +328,22 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     // ---- (2) constraint evaluation ----
     {
         ConstraintParams hp{};
-        for (uint32_t j = 0; j < kTransitions; j++) put(hp.tcoef[j], coin.draw());
+        for (uint32_t j = 0; j < kTransitions; j++) {
+            const Fp c = coin.draw();
+            put(hp.tcoef[j], c), put_pre(hp.tcoef_pre[j], c);
+        }
         Fp bc[kAssertions];
         for (uint32_t k = 0; k < kAssertions; k++) bc[k] = coin.draw();
         // assertions sorted by (step, column): air/src/lib.rs:170-195 + winter-air's prepare_assertions
         const uint32_t cols0[12] = {0, 7, 8, 11, 12, 13, 14, 15, 16, 17, 18, 19};
         const uint32_t cols1[10] = {7, 8, 12, 13, 14, 15, 16, 17, 18, 19};
         for (uint32_t k = 0; k < 12; k++) {
-            put(hp.bcoef[k], bc[k]);
+            put(hp.bcoef[k], bc[k]), put_pre(hp.bcoef_pre[k], bc[k]);
             put(hp.bval[k], Fp());
             hp.bcol[k] = cols0[k];
         }
         for (uint32_t k = 0; k < 10; k++) {
-            put(hp.bcoef[12 + k], bc[12 + k]);
+            put(hp.bcoef[12 + k], bc[12 + k]), put_pre(hp.bcoef_pre[12 + k], bc[12 + k]);
             // values: program_hash[0..2] for columns 7,8; stack_outputs[0..8] for columns 12..19
             put(hp.bval[12 + k], k < 2 ? pub.elements[k] : pub.elements[2 + (k - 2)]);
             hp.bcol[12 + k] = cols1[k];
@@ -346,7 +357,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
             w8c = w8c * w8;
         }
         put(hp.g_last, g_last), put(hp.g_last2, g_last2);
-        for (int i = 0; i < 16; i++) put(hp.inv_mds[i], rescue_const(rescue_inv_mds()[i]));
+        for (int i = 0; i < 16; i++) put(hp.inv_mds[i], rescue_const(rescue_inv_mds()[i])), put_pre(hp.inv_mds_pre[i], rescue_const(rescue_inv_mds()[i]));
         // periodic columns: mask + 8 ARK columns (air/src/lib.rs:201-225, rescue.rs:120-134), interpolated over
         // <w_16> and tabulated at x^(n/16) for the 128 distinct values of step mod 128
         // (depends on n only: cached per trace length, 1152 Horner evaluations otherwise)
@@ -745,7 +756,7 @@ void GpuProver::stage_eval_frames(const void* cur, const void* nxt, const void* 
     EZK_CUDA(cudaMemcpyAsync(d_p, periodic, (size_t)nframes * 9 * 16, cudaMemcpyHostToDevice, stream_));
     ConstraintParams hp{};
     hp.delta = delta;
-    for (int i = 0; i < 16; i++) put(hp.inv_mds[i], rescue_const(rescue_inv_mds()[i]));
+    for (int i = 0; i < 16; i++) put(hp.inv_mds[i], rescue_const(rescue_inv_mds()[i])), put_pre(hp.inv_mds_pre[i], rescue_const(rescue_inv_mds()[i]));
     EZK_CUDA(cudaMemcpyAsync(d_params_, &hp, sizeof(hp), cudaMemcpyHostToDevice, stream_));
     evaluate_frames(stream_, d_c, d_n, d_p, nframes, d_params_, d_o);
     EZK_CUDA(cudaMemcpyAsync(out20, d_o, (size_t)nframes * 20 * 16, cudaMemcpyDeviceToHost, stream_));
