@@ -170,15 +170,22 @@ __device__ __forceinline__ bool group_compute(const Pass& P, const uint4* tile, 
                                               uint32_t q, uint32_t jg, fe (&x)[8]) {
     Arith<FAST> ar;
     const uint32_t sh = c.log_cur - 3;
+    // slot p of the group sits at a fixed stride from slot 0: one base address per group, p * step per slot
+    if (c.first) {
+        const typename Pass::In in = P.begin_in(lane, i0, sh);
 #pragma unroll
-    for (int p = 0; p < 8; p++) {
-        const uint32_t i = i0 + ((uint32_t)p << sh);
-        x[p] = c.first ? P.load(ar, lane, i) : fe_load(tile + (i << c.lanes_log) + lane);
+        for (int p = 0; p < 8; p++) x[p] = P.load(ar, in, p);
+    } else {
+        const uint4* t0 = tile + (i0 << c.lanes_log) + lane;
+        const uint32_t step = (1u << sh) << c.lanes_log;
+#pragma unroll
+        for (int p = 0; p < 8; p++) x[p] = fe_load(t0 + p * step);
     }
     radix_step(ar, x, c.a, c.log_cur, q, c.inv, c.tw);
     if (c.last) {
+        const typename Pass::Out out = P.begin_out(lane, jg, c.log_s);
 #pragma unroll
-        for (int p = 0; p < 8; p++) x[p] = P.finish(ar, lane, jg + ((uint32_t)p << (c.log_s - 3)), x[p]);
+        for (int p = 0; p < 8; p++) x[p] = P.finish(ar, out, p, x[p]);
     }
     return ar.tainted();
 }
@@ -187,12 +194,14 @@ template <class Pass>
 __device__ __forceinline__ void group_store(const Pass& P, uint4* tile, const StepCtx& c, uint32_t lane, uint32_t i0,
                                             uint32_t jg, const fe (&x)[8]) {
     if (c.last) {
+        const typename Pass::Out out = P.begin_out(lane, jg, c.log_s);
 #pragma unroll
-        for (int p = 0; p < 8; p++) P.store(lane, jg + ((uint32_t)p << (c.log_s - 3)), x[p]);
+        for (int p = 0; p < 8; p++) P.store(out, p, x[p]);
     } else {
-        const uint32_t sh = c.log_cur - 3;
+        uint4* t0 = tile + (i0 << c.lanes_log) + lane;
+        const uint32_t step = (1u << (c.log_cur - 3)) << c.lanes_log;
 #pragma unroll
-        for (int p = 0; p < 8; p++) fe_store(tile + ((i0 + ((uint32_t)p << sh)) << c.lanes_log) + lane, x[p]);
+        for (int p = 0; p < 8; p++) fe_store(t0 + p * step, x[p]);
     }
 }
 
@@ -268,22 +277,48 @@ struct StridedPass {
     // LDE first pass: the coset factor w_L^(c * idx), idx = lo + stride * m, splits into w_L^(c * stride * m)
     // (applied on load: exponent with >= 14 trailing zero bits in the 2^28 table -> one load, no product) and
     // w_L^(c * lo), constant along the transform, which is folded into the output twiddle's exponent:
-    // w_N^(lo j) w_L^(c lo) = w_L^(lo (8 j + c)).
+    // w_N^(lo j) w_L^(c lo) = w_L^(lo (8 j + coset)).
+    struct In {
+        const uint4* ptr;   // slot 0
+        uint64_t step;      // elements between slots
+        uint32_t m0, mstep; // transform index of slot 0 / between slots (coset factor)
+    };
+    struct Out {
+        uint4* ptr;
+        const uint4* tab;   // slot 0 of the inter-pass twiddle table (same slot stride as the data), or nullptr
+        uint64_t step;
+        uint32_t lo, j0, jstep;
+    };
+    __device__ __forceinline__ In begin_in(uint32_t lane, uint32_t i0, uint32_t sh) const {
+        In in;
+        in.ptr = src + base + lane + ((uint64_t)i0 << log_stride);
+        in.step = 1ull << (sh + log_stride);
+        in.m0 = i0, in.mstep = 1u << sh;
+        return in;
+    }
     template <class A>
-    __device__ __forceinline__ fe load(A& ar, uint32_t lane, uint32_t m) const {
-        fe v = fe_load(src + base + lane + ((uint64_t)m << log_stride));
+    __device__ __forceinline__ fe load(A& ar, const In& in, int p) const {
+        fe v = fe_load(in.ptr + p * in.step);
+        const uint32_t m = in.m0 + p * in.mstep;
         if (coset != 0 && m != 0) v = ar.mul(v, root_pow(ar, roots, log_L, ((uint64_t)coset * m) << log_stride));
         return v;
     }
+    __device__ __forceinline__ Out begin_out(uint32_t lane, uint32_t jg, uint32_t log_s) const {
+        Out out;
+        const uint64_t at = ((uint64_t)jg << log_stride) + lo0 + lane;
+        out.ptr = dst + base - lo0 + at;
+        out.step = 1ull << (log_s - 3 + log_stride);
+        out.tab = big ? big + ((uint64_t)coset << log_N) + at : nullptr;
+        out.lo = lo0 + lane, out.j0 = jg, out.jstep = 1u << (log_s - 3);
+        return out;
+    }
     template <class A>
-    __device__ __forceinline__ fe finish(A& ar, uint32_t lane, uint32_t j, fe v) const {
-        if (big) return ar.mul(v, fe_ldg(big + ((uint64_t)coset << log_N) + ((uint64_t)j << log_stride) + lo0 + lane));
-        const uint64_t ex = (uint64_t)(lo0 + lane) * (((uint64_t)j << (log_L - log_N)) + coset);
+    __device__ __forceinline__ fe finish(A& ar, const Out& out, int p, fe v) const {
+        if (out.tab) return ar.mul(v, fe_ldg(out.tab + p * out.step));
+        const uint64_t ex = (uint64_t)out.lo * (((uint64_t)(out.j0 + p * out.jstep) << (log_L - log_N)) + coset);
         return ex != 0 ? ar.mul(v, root_pow(ar, roots, log_L, ex)) : v;
     }
-    __device__ __forceinline__ void store(uint32_t lane, uint32_t j, fe v) const {
-        fe_store(dst + base + lane + ((uint64_t)j << log_stride), v);
-    }
+    __device__ __forceinline__ void store(const Out& out, int p, fe v) const { fe_store(out.ptr + p * out.step, v); }
 };
 
 template <int THREADS, int MINB>
@@ -337,24 +372,50 @@ struct FinalPass {
     uint4* dst;
     uint64_t run0, run_step, out_base;
     uint32_t log_H, coset0;
+    struct In {
+        const uint4* ptr;
+        uint32_t step, m0, coset;
+    };
+    struct Out {
+        uint4* ptr;
+        uint64_t step, index;  // elements between slots / output index of slot 0 (for the scaling)
+    };
+    __device__ __forceinline__ In begin_in(uint32_t lane, uint32_t i0, uint32_t sh) const {
+        In in;
+        in.step = 1u << sh, in.m0 = i0, in.coset = 0;
+        if (a->mode == 0) {
+            in.ptr = src + ((run0 + lane * run_step) << a->log_s) + i0;
+        } else if (a->mode == 1) {
+            // coset0 + lane = index into this prover's coset list; the coset itself is cs_base + cs_step * index
+            in.ptr = src + (uint64_t)(coset0 + lane) * a->src_pitch + (run0 << a->log_s) + i0;
+        } else {
+            in.ptr = src + i0;
+            in.coset = a->cs_base + a->cs_step * (coset0 + lane);
+        }
+        return in;
+    }
     template <class A>
-    __device__ __forceinline__ fe load(A& ar, uint32_t lane, uint32_t m) const {
-        if (a->mode == 0) return fe_load(src + ((run0 + lane * run_step) << a->log_s) + m);
-        // coset0 + lane = index into this prover's coset list; the coset itself is cs_base + cs_step * index
-        if (a->mode == 1) return fe_load(src + (uint64_t)(coset0 + lane) * a->src_pitch + (run0 << a->log_s) + m);
-        const uint32_t coset = a->cs_base + a->cs_step * (coset0 + lane);
-        fe v = fe_load(src + m);
-        if (coset != 0) v = ar.mul(v, root_pow(ar, a->roots, a->log_L, (uint64_t)coset * m));
+    __device__ __forceinline__ fe load(A& ar, const In& in, int p) const {
+        fe v = fe_load(in.ptr + p * in.step);
+        if (in.coset != 0) v = ar.mul(v, root_pow(ar, a->roots, a->log_L, (uint64_t)in.coset * (in.m0 + p * in.step)));
         return v;
     }
-    __device__ __forceinline__ uint64_t out_index(uint32_t lane, uint32_t j1) const {
-        if (a->mode == 0) return ((uint64_t)j1 << log_H) + out_base + lane;
-        return ((((uint64_t)j1 << log_H) + out_base) << 3) + a->cs_base + a->cs_step * (coset0 + lane);
+    __device__ __forceinline__ Out begin_out(uint32_t lane, uint32_t jg, uint32_t log_s) const {
+        Out out;
+        if (a->mode == 0) {
+            out.index = ((uint64_t)jg << log_H) + out_base + lane;
+            out.step = 1ull << (log_s - 3 + log_H);
+        } else {
+            out.index = ((((uint64_t)jg << log_H) + out_base) << 3) + a->cs_base + a->cs_step * (coset0 + lane);
+            out.step = 1ull << (log_s - 3 + log_H + 3);
+        }
+        out.ptr = dst + out.index;
+        return out;
     }
     template <class A>
-    __device__ __forceinline__ fe finish(A& ar, uint32_t lane, uint32_t j1, fe v) const {
+    __device__ __forceinline__ fe finish(A& ar, const Out& o, int p, fe v) const {
         if (a->mode == 0 && a->scale.enabled) {
-            const uint64_t out = out_index(lane, j1);
+            const uint64_t out = o.index + p * o.step;
             const uint32_t ci = (uint32_t)(out >> a->scale.chunk_shift);
             fe c = fe_make(a->scale.cvec[ci][0], a->scale.cvec[ci][1]);
             if (a->scale.use_offset) c = ar.mul(c, tab_pow(ar, a->off_tab, (uint32_t)out));
@@ -362,7 +423,7 @@ struct FinalPass {
         }
         return v;
     }
-    __device__ __forceinline__ void store(uint32_t lane, uint32_t j1, fe v) const { fe_store(dst + out_index(lane, j1), v); }
+    __device__ __forceinline__ void store(const Out& o, int p, fe v) const { fe_store(o.ptr + p * o.step, v); }
 };
 
 template <int THREADS, int MINB>
