@@ -53,7 +53,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, device_index: int):
         self.device_index = device_index
@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -76,21 +76,24 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, smax, reasons = [], [], set()
+        rows, smax = [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1])), smax.append(float(parts[2]))
+                clk, util = float(parts[1]), float(parts[9])
+                smax.append(float(parts[2]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+            rows.append((clk, util, {name for name, val in zip(names, parts[5:9]) if val.lower().startswith("active")}))
+        # the sampler runs from before the warm-up proofs: keep the samples taken under load
+        loaded = [r for r in rows if r[1] >= 50.0] or rows
+        reasons = set().union(*[r[2] for r in loaded]) if loaded else set()
+        sm = [r[0] for r in loaded]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_total": len(rows), "reasons": sorted(reasons)}
 
 
 def cpu_oracle_run(log_n: int, kind: int, threads: int, repeats: int = 1):
@@ -222,14 +225,17 @@ def main():
     prover = ezk.ExecutionProver(ezk.ProofOptions(), program_hash, outputs, ezk.ServerKey(), device=local_rank)
 
     # ---- device-resident arm ----
+    # the clock sampler starts before the warm-up proofs (nvidia-smi needs ~0.2 s to deliver its first sample and the
+    # timed region of a few proofs is shorter than that); warm-up and timed steps run the same kernels back to back
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
     for _ in range(max(args.warmup, 3)):
         proof = prover.prove_device(dev.data_ptr(), n)
-    sampler = ClockSampler(local_rank)
     ezk.profile_enable(True)
     ezk.profile_reset()
     barrier()
     launches0 = ezk.kernel_launch_count()
-    sampler.start()
     prover.timer_start()
     for _ in range(args.steps):
         proof = prover.prove_device(dev.data_ptr(), n)

@@ -283,7 +283,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         if (host_columns) {
             // Upload and transform in column groups: the copy of group k+1 (copy stream) overlaps the
             // interpolation + LDE of group k (compute stream).  Columns are independent until the row hash.
-            constexpr uint32_t kGroup = 7;
+            constexpr uint32_t kGroup = 2;  // small groups: the pipeline fills after 2 columns (32 MiB at 2^20), not 7
             EZK_CUDA(cudaEventRecord(copy_ev_[kWidth / kGroup], stream_));
             EZK_CUDA(cudaStreamWaitEvent(copy_stream_, copy_ev_[kWidth / kGroup], 0));  // the arena may still be in use
             for (uint32_t g = 0; g < kWidth / kGroup; g++) {

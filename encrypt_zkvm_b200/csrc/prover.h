@@ -67,7 +67,7 @@ private:
     int device_;
     cudaStream_t stream_ = nullptr;
     cudaStream_t copy_stream_ = nullptr;  // host -> device trace upload, overlapped with the first transforms
-    cudaEvent_t copy_ev_[5];
+    cudaEvent_t copy_ev_[16];
     cudaStream_t aux_stream_ = nullptr;   // small independent kernels overlapped with latency-bound phases
     cudaEvent_t aux_ev_[4];
     NttTables tables_;
