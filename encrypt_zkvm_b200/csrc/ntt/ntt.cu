@@ -41,8 +41,18 @@ inline unsigned threads_for(uint32_t log_s, uint32_t lanes_log, unsigned max_thr
     return t < 32 ? 32 : t;
 }
 
-// w_8^1..3 for the in-register 8-point butterflies: [0] forward, [1] inverse
-__constant__ uint4 c_w8[2][4];
+// w_8^1..3 for the in-register 8-point butterflies: [0] forward, [1] inverse, in precomputed form
+// (c_w8pre[d][k][i] = w_8^(+-k) * 2^(32 i) mod M, see fe_mul_pre).  The direction is a template parameter, so every
+// limb is a constant-bank operand of the IMAD.WIDE that uses it: no load, no register.
+__constant__ uint4 c_w8pre[2][4][4];
+
+template <int INV, int K>
+__device__ __forceinline__ fe_pre w8_pre() {
+    fe_pre r;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.w[i] = fe_from(c_w8pre[INV][K][i]);
+    return r;
+}
 
 // compact per-size twiddle tables: tw[(1 << k) + e] = w_{2^k}^e, e < 2^k, k <= kTwMaxLog
 constexpr uint32_t kTwMaxLog = 11;
@@ -75,23 +85,27 @@ __device__ __forceinline__ void bf_w(A& ar, fe& a, fe& b, const fe& w) {
     fe s = ar.add(a, b), d = ar.sub(a, b);
     a = s, b = ar.mul(d, w);
 }
+template <class A>
+__device__ __forceinline__ void bf_pre(A& ar, fe& a, fe& b, const fe_pre& w) {
+    fe s = ar.add(a, b), d = ar.sub(a, b);
+    a = s, b = ar.mul_pre(d, w);
+}
 __device__ __forceinline__ void swap_fe(fe& a, fe& b) {
     fe t = a;
     a = b, b = t;
 }
 
 // x[k] <- sum_p x[p] w_8^(pk): three decimation-in-frequency stages on registers, 5 constant multiplications
-template <class A>
-__device__ __forceinline__ void dft8(A& ar, fe (&x)[8], uint32_t inv) {
-    const fe w1 = fe_from(c_w8[inv][1]), w2 = fe_from(c_w8[inv][2]), w3 = fe_from(c_w8[inv][3]);
+template <int INV, class A>
+__device__ __forceinline__ void dft8(A& ar, fe (&x)[8]) {
     bf(ar, x[0], x[4]);
-    bf_w(ar, x[1], x[5], w1);
-    bf_w(ar, x[2], x[6], w2);
-    bf_w(ar, x[3], x[7], w3);
+    bf_pre(ar, x[1], x[5], w8_pre<INV, 1>());
+    bf_pre(ar, x[2], x[6], w8_pre<INV, 2>());
+    bf_pre(ar, x[3], x[7], w8_pre<INV, 3>());
     bf(ar, x[0], x[2]);
-    bf_w(ar, x[1], x[3], w2);
+    bf_pre(ar, x[1], x[3], w8_pre<INV, 2>());
     bf(ar, x[4], x[6]);
-    bf_w(ar, x[5], x[7], w2);
+    bf_pre(ar, x[5], x[7], w8_pre<INV, 2>());
     bf(ar, x[0], x[1]);
     bf(ar, x[2], x[3]);
     bf(ar, x[4], x[5]);
@@ -102,11 +116,10 @@ __device__ __forceinline__ void dft8(A& ar, fe (&x)[8], uint32_t inv) {
 }
 
 // 4-point DFT of (m0..m3): X_k = sum_j m_j w_4^(jk), returned in natural order in the same registers
-template <class A>
-__device__ __forceinline__ void dft4(A& ar, fe& m0, fe& m1, fe& m2, fe& m3, uint32_t inv) {
-    const fe w2 = fe_from(c_w8[inv][2]);  // w_4
+template <int INV, class A>
+__device__ __forceinline__ void dft4(A& ar, fe& m0, fe& m1, fe& m2, fe& m3) {
     bf(ar, m0, m2);
-    bf_w(ar, m1, m3, w2);
+    bf_pre(ar, m1, m3, w8_pre<INV, 2>());  // w_4
     bf(ar, m0, m1);
     bf(ar, m2, m3);
     swap_fe(m1, m2);
@@ -115,20 +128,20 @@ __device__ __forceinline__ void dft4(A& ar, fe& m0, fe& m1, fe& m2, fe& m3, uint
 // One radix-2^a step (a = 1, 2, 3) of a decimation-in-frequency transform of size 2^log_cur on the 8 registers a
 // thread holds: slot p (p = 0..7) is position q + p * 2^(log_cur-3) of the sub-transform.  On return x[p'] is the
 // value to put back into slot p' (in place), already multiplied by its twiddle w_{2^log_cur}^(q' m').
-template <class A>
-__device__ __forceinline__ void radix_step(A& ar, fe (&x)[8], uint32_t a, uint32_t log_cur, uint32_t q, uint32_t inv,
+template <int INV, class A>
+__device__ __forceinline__ void radix_step(A& ar, fe (&x)[8], uint32_t a, uint32_t log_cur, uint32_t q,
                                            const uint4* __restrict__ tw) {
     const uint32_t eighth = 1u << (log_cur - 3);
     if (a == 3) {
-        dft8(ar, x, inv);
+        dft8<INV>(ar, x);
         if (log_cur > 3 && q != 0) {
 #pragma unroll
             for (int k = 1; k < 8; k++) x[k] = ar.mul(x[k], tw_at(tw, log_cur, q * k));
         }
     } else if (a == 2) {
         // two 4-point butterflies: h = p & 1 selects q' = q + h * eighth, m = p >> 1 is the digit
-        dft4(ar, x[0], x[2], x[4], x[6], inv);
-        dft4(ar, x[1], x[3], x[5], x[7], inv);
+        dft4<INV>(ar, x[0], x[2], x[4], x[6]);
+        dft4<INV>(ar, x[1], x[3], x[5], x[7]);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint32_t qq = q + h * eighth;
@@ -158,14 +171,14 @@ __device__ __forceinline__ uint32_t digit_reverse(uint32_t i, uint32_t log_s, ui
 }
 
 struct StepCtx {
-    uint32_t log_s, lanes_log, inv, a, a1, log_cur, first, last;
+    uint32_t log_s, lanes_log, a, a1, log_cur, first, last;
     const uint4* tw;
 };
 
 // One group of 8 elements of one step: gather (global memory through P.load on the first step, shared memory
 // otherwise), butterflies, and on the last step the pass's output factor (P.finish).  Returns true when a FAST
 // computation hit a rare tail and must be redone.
-template <bool FAST, class Pass>
+template <bool FAST, int INV, class Pass>
 __device__ __forceinline__ bool group_compute(const Pass& P, const uint4* tile, const StepCtx& c, uint32_t lane, uint32_t i0,
                                               uint32_t q, uint32_t jg, fe (&x)[8]) {
     Arith<FAST> ar;
@@ -181,7 +194,7 @@ __device__ __forceinline__ bool group_compute(const Pass& P, const uint4* tile, 
 #pragma unroll
         for (int p = 0; p < 8; p++) x[p] = fe_load(t0 + p * step);
     }
-    radix_step(ar, x, c.a, c.log_cur, q, c.inv, c.tw);
+    radix_step<INV>(ar, x, c.a, c.log_cur, q, c.tw);
     if (c.last) {
         const typename Pass::Out out = P.begin_out(lane, jg, c.log_s);
 #pragma unroll
@@ -206,11 +219,11 @@ __device__ __forceinline__ void group_store(const Pass& P, uint4* tile, const St
 }
 
 // the rare redo: exact arithmetic, computes and stores the group (kept out of line, off the hot path's registers)
-template <class Pass>
+template <int INV, class Pass>
 __device__ __noinline__ void group_redo_exact(const Pass& P, uint4* tile, const StepCtx& c, uint32_t lane, uint32_t i0,
                                               uint32_t q, uint32_t jg) {
     fe x[8];
-    group_compute<false>(P, tile, c, lane, i0, q, jg, x);
+    group_compute<false, INV>(P, tile, c, lane, i0, q, jg, x);
     group_store(P, tile, c, lane, i0, jg, x);
 }
 
@@ -218,12 +231,12 @@ __device__ __noinline__ void group_redo_exact(const Pass& P, uint4* tile, const 
 // registers per step; steps exchange through shared memory (tile[i * lanes + lane], lanes fastest so that a
 // quarter-warp always touches 8 consecutive 16-byte words); the first step reads global memory through
 // P.load(lane, i) and the last writes through P.store(lane, j, v) with j the natural frequency index.
-template <class Pass>
-__device__ __forceinline__ void tile_transform(const Pass& P, uint4* tile, uint32_t log_s, uint32_t lanes_log, uint32_t inv,
+template <int INV, class Pass>
+__device__ __forceinline__ void tile_transform(const Pass& P, uint4* tile, uint32_t log_s, uint32_t lanes_log,
                                                const uint4* __restrict__ tw) {
     const uint32_t steps = (log_s + 2) / 3;
     StepCtx c;
-    c.log_s = log_s, c.lanes_log = lanes_log, c.inv = inv, c.tw = tw;
+    c.log_s = log_s, c.lanes_log = lanes_log, c.tw = tw;
     c.a1 = log_s - 3 * (steps - 1);
     c.log_cur = log_s;
     const uint32_t groups = (1u << (log_s - 3)) << lanes_log;
@@ -239,8 +252,8 @@ __device__ __forceinline__ void tile_transform(const Pass& P, uint4* tile, uint3
             // last step (sh == 0): i = 8 g + p and the last digit is the most significant part of the frequency
             const uint32_t jg = c.last ? digit_reverse(i0, log_s, c.a1) : 0;
             fe x[8];
-            if (group_compute<true>(P, tile, c, lane, i0, q, jg, x))
-                group_redo_exact(P, tile, c, lane, i0, q, jg);
+            if (group_compute<true, INV>(P, tile, c, lane, i0, q, jg, x))
+                group_redo_exact<INV>(P, tile, c, lane, i0, q, jg);
             else
                 group_store(P, tile, c, lane, i0, jg, x);
         }
@@ -321,7 +334,7 @@ struct StridedPass {
     __device__ __forceinline__ void store(const Out& out, int p, fe v) const { fe_store(out.ptr + p * out.step, v); }
 };
 
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, int INV>
 __global__ void __launch_bounds__(THREADS, MINB) ntt_strided_pass(StridedArgs a) {
     extern __shared__ uint4 tile[];
     const uint32_t lanes = 1u << a.lanes_log;
@@ -343,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_strided_pass(StridedArgs a)
     P.big = a.big;
     P.log_stride = a.log_stride, P.log_N = a.log_stride + a.log_s;
     P.log_L = a.coset_first ? a.log_L : P.log_N;  // plain passes: exponent lo * j of w_N
-    tile_transform(P, tile, a.log_s, a.lanes_log, a.inv, a.tw);
+    tile_transform<INV>(P, tile, a.log_s, a.lanes_log, a.tw);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -426,7 +439,7 @@ struct FinalPass {
     __device__ __forceinline__ void store(const Out& o, int p, fe v) const { fe_store(o.ptr + p * o.step, v); }
 };
 
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, int INV>
 __global__ void __launch_bounds__(THREADS, MINB) ntt_final_pass(const __grid_constant__ FinalArgs a) {
     extern __shared__ uint4 tile[];
     const uint32_t lanes = 1u << a.lanes_log;
@@ -465,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_final_pass(const __grid_con
             P.out_base = (rest << a.log_top) + jp;
         }
     }
-    tile_transform(P, tile, a.log_s, a.lanes_log, a.inv, a.tw);
+    tile_transform<INV>(P, tile, a.log_s, a.lanes_log, a.tw);
 }
 
 // n = 2 or 4 (single run, fewer points than one 8-element register group): direct summation, one thread per output
@@ -510,33 +523,51 @@ Plan make_plan(uint32_t log_n, int max_tile_log) {
 
 // launch shapes: 0 = 256 threads x 3 CTAs/SM (<= 85 registers), 1 = 512 threads x 2 CTAs/SM (<= 64 registers)
 int g_variant = -1;
+template <int T, int B, int INV>
+void set_smem_attr() {
+    const int bytes = (int)(kTileElems * 16);
+    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass<T, B, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass<T, B, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+}
 void ensure_smem_attr() {
     if (g_variant >= 0) return;
-    const int bytes = (int)(kTileElems * 16);
-    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    EZK_CUDA(cudaFuncSetAttribute(ntt_strided_pass<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    EZK_CUDA(cudaFuncSetAttribute(ntt_final_pass<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    set_smem_attr<256, 3, 0>(), set_smem_attr<256, 3, 1>();
+    set_smem_attr<512, 2, 0>(), set_smem_attr<512, 2, 1>();
+    set_smem_attr<256, 2, 0>(), set_smem_attr<256, 2, 1>();
     const char* env = getenv("EZK_NTT_VARIANT");
     g_variant = env ? atoi(env) : 0;
 }
+template <int T, int B>
+void launch_strided_tb(dim3 grid, size_t smem, cudaStream_t s, const StridedArgs& a) {
+    const unsigned threads = threads_for(a.log_s, a.lanes_log, T);
+    if (a.inv)
+        ntt_strided_pass<T, B, 1><<<grid, threads, smem, s>>>(a);
+    else
+        ntt_strided_pass<T, B, 0><<<grid, threads, smem, s>>>(a);
+}
+template <int T, int B>
+void launch_final_tb(dim3 grid, size_t smem, cudaStream_t s, const FinalArgs& a) {
+    const unsigned threads = threads_for(a.log_s, a.lanes_log, T);
+    if (a.inv)
+        ntt_final_pass<T, B, 1><<<grid, threads, smem, s>>>(a);
+    else
+        ntt_final_pass<T, B, 0><<<grid, threads, smem, s>>>(a);
+}
 void launch_strided(dim3 grid, size_t smem, cudaStream_t s, const StridedArgs& a) {
     if (g_variant == 1)
-        ntt_strided_pass<512, 2><<<grid, threads_for(a.log_s, a.lanes_log, 512), smem, s>>>(a);
+        launch_strided_tb<512, 2>(grid, smem, s, a);
     else if (g_variant == 2)
-        ntt_strided_pass<256, 2><<<grid, threads_for(a.log_s, a.lanes_log, 256), smem, s>>>(a);
+        launch_strided_tb<256, 2>(grid, smem, s, a);
     else
-        ntt_strided_pass<256, 3><<<grid, threads_for(a.log_s, a.lanes_log, 256), smem, s>>>(a);
+        launch_strided_tb<256, 3>(grid, smem, s, a);
 }
 void launch_final(dim3 grid, size_t smem, cudaStream_t s, const FinalArgs& a) {
     if (g_variant == 1)
-        ntt_final_pass<512, 2><<<grid, threads_for(a.log_s, a.lanes_log, 512), smem, s>>>(a);
+        launch_final_tb<512, 2>(grid, smem, s, a);
     else if (g_variant == 2)
-        ntt_final_pass<256, 2><<<grid, threads_for(a.log_s, a.lanes_log, 256), smem, s>>>(a);
+        launch_final_tb<256, 2>(grid, smem, s, a);
     else
-        ntt_final_pass<256, 3><<<grid, threads_for(a.log_s, a.lanes_log, 256), smem, s>>>(a);
+        launch_final_tb<256, 3>(grid, smem, s, a);
 }
 
 // Full inter-pass twiddle table of one strided pass: entry (c << log_N) + (j << log_stride) + lo =
@@ -659,9 +690,13 @@ void ntt_tables_init(NttTables& t) {
     std::vector<Fp> cf = build_compact(false), ci = build_compact(true);
     t.tw_fwd = upload(cf);
     t.tw_inv = upload(ci);
-    Fp w8[2][4];
-    for (int e = 0; e < 4; e++) w8[0][e] = cf[8 + e], w8[1][e] = ci[8 + e];
-    EZK_CUDA(cudaMemcpyToSymbol(c_w8, w8, sizeof(w8)));
+    Fp w8[2][4][4];
+    const Fp two32 = Fp::from_u64(1ull << 32);
+    for (int e = 0; e < 4; e++) {
+        w8[0][e][0] = cf[8 + e], w8[1][e][0] = ci[8 + e];
+        for (int i = 1; i < 4; i++) w8[0][e][i] = w8[0][e][i - 1] * two32, w8[1][e][i] = w8[1][e][i - 1] * two32;
+    }
+    EZK_CUDA(cudaMemcpyToSymbol(c_w8pre, w8, sizeof(w8)));
     t.big_tables = new std::map<uint64_t, uint4*>();
     if (const char* e = getenv("EZK_NTT_BIG_TABLE_MB")) t.big_table_limit_bytes = (uint64_t)atoll(e) << 20;
     const char* env = getenv("EZK_NTT_TILE_LOG");
