@@ -12,38 +12,59 @@ namespace {
 constexpr int kEvalThreads = 256;
 constexpr uint32_t kEvalChunkLog = 14;  // coefficients per block
 
-// block (bx, col): partial sums over coefficients [bx*chunk, (bx+1)*chunk) at up to 2 points.
-// thread t owns m = base + t + q*T: acc = sum_q a[m] Y^q (Horner, Y = y^T), then times y^(base + t).
-__global__ void __launch_bounds__(kEvalThreads) eval_partial_kernel(const uint4* __restrict__ coeff, uint64_t pitch,
-                                                                   uint32_t log_n, fe y0, fe y1, uint32_t npoints,
-                                                                   uint4* __restrict__ scratch) {
-    __shared__ uint4 red[2][kEvalThreads];
+// pw[k][m] = y_k^m for m < n, k < npoints.  Thread t of a block starts from y^(base + t) (square-and-multiply) and
+// walks its residue class with one product per entry.
+__global__ void __launch_bounds__(kEvalThreads) power_table_kernel(uint32_t log_n, fe y0, fe y1, uint32_t npoints,
+                                                                  uint4* __restrict__ pw) {
     const uint64_t n = 1ull << log_n;
     const uint64_t chunk = n < (1ull << kEvalChunkLog) ? n : (1ull << kEvalChunkLog);
     const uint64_t base = (uint64_t)blockIdx.x * chunk;
-    const uint4* col = coeff + (uint64_t)blockIdx.y * pitch;
     const uint32_t T = blockDim.x, t = threadIdx.x;
-    fe ys[2] = {y0, y1};
-    fe acc[2] = {fe_zero(), fe_zero()};
-    if (t < chunk) {
-        fe Y[2];
-        for (uint32_t k = 0; k < npoints; k++) Y[k] = fe_pow(ys[k], T);
-        const uint64_t iters = (chunk - t + T - 1) / T;
-        for (uint64_t q = iters; q-- > 0;) {
-            fe a = fe_ldg(col + base + t + q * T);
-            for (uint32_t k = 0; k < npoints; k++) acc[k] = fe_add(fe_mul(acc[k], Y[k]), a);
+    if (t >= chunk) return;
+    const fe ys[2] = {y0, y1};
+    for (uint32_t k = 0; k < npoints; k++) {
+        const fe Y = fe_pow(ys[k], T);
+        fe p = fe_pow(ys[k], base + t);
+        uint4* dst = pw + (uint64_t)k * n + base;
+        for (uint64_t m = t; m < chunk; m += T) {
+            fe_store(dst + m, p);
+            p = fe_mul(p, Y);
         }
-        for (uint32_t k = 0; k < npoints; k++) acc[k] = fe_mul(acc[k], fe_pow(ys[k], base + t));
     }
-    for (uint32_t k = 0; k < npoints; k++) fe_store(&red[k][t], acc[k]);
+}
+
+// block (bx, col): partial dot products of coefficients [bx*chunk, (bx+1)*chunk) with the power tables of up to 2
+// points.  Every term is independent (no Horner chain), so the products of a thread overlap.
+template <int NP>
+__global__ void __launch_bounds__(kEvalThreads) eval_partial_kernel(const uint4* __restrict__ coeff, uint64_t pitch,
+                                                                   uint32_t log_n, const uint4* __restrict__ pw,
+                                                                   uint4* __restrict__ scratch) {
+    __shared__ uint4 red[NP][kEvalThreads];
+    const uint64_t n = 1ull << log_n;
+    const uint64_t chunk = n < (1ull << kEvalChunkLog) ? n : (1ull << kEvalChunkLog);
+    const uint64_t base = (uint64_t)blockIdx.x * chunk;
+    const uint4* col = coeff + (uint64_t)blockIdx.y * pitch + base;
+    const uint32_t T = blockDim.x, t = threadIdx.x;
+    fe acc[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) acc[k] = fe_zero();
+#pragma unroll 4
+    for (uint64_t m = t; m < chunk; m += T) {
+        const fe a = fe_ldg(col + m);
+#pragma unroll
+        for (int k = 0; k < NP; k++) acc[k] = fe_add(acc[k], fe_mul(a, fe_ldg(pw + (uint64_t)k * n + base + m)));
+    }
+#pragma unroll
+    for (int k = 0; k < NP; k++) fe_store(&red[k][t], acc[k]);
     __syncthreads();
     for (uint32_t h = T / 2; h >= 1; h >>= 1) {
-        if (t < h)
-            for (uint32_t k = 0; k < npoints; k++)
-                fe_store(&red[k][t], fe_add(fe_load(&red[k][t]), fe_load(&red[k][t + h])));
+        if (t < h) {
+#pragma unroll
+            for (int k = 0; k < NP; k++) fe_store(&red[k][t], fe_add(fe_load(&red[k][t]), fe_load(&red[k][t + h])));
+        }
         __syncthreads();
     }
-    if (t < npoints) scratch[((uint64_t)blockIdx.y * npoints + t) * gridDim.x + blockIdx.x] = red[t][0];
+    if (t < NP) scratch[((uint64_t)blockIdx.y * NP + t) * gridDim.x + blockIdx.x] = red[t][0];
 }
 
 __global__ void eval_final_kernel(const uint4* __restrict__ scratch, uint32_t nblocks, uint32_t nout,
@@ -109,14 +130,26 @@ __global__ void canonical_kernel(const uint4* __restrict__ v, uint64_t count, ui
 
 }  // namespace
 
-int eval_polys(cudaStream_t s, const uint4* coeff, uint64_t pitch, uint32_t ncols, uint32_t log_n, const uint64_t y[2][2],
+int power_table(cudaStream_t s, uint32_t log_n, const uint64_t y[2][2], uint32_t npoints, uint4* pw) {
+    uint32_t nblocks = log_n > kEvalChunkLog ? 1u << (log_n - kEvalChunkLog) : 1;
+    {
+        LaunchScope ls(s, K_EVAL_POLYS, ((uint64_t)npoints << log_n) * 16);
+        power_table_kernel<<<nblocks, kEvalThreads, 0, s>>>(log_n, fe_make(y[0][0], y[0][1]), fe_make(y[1][0], y[1][1]), npoints, pw);
+    }
+    EZK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+int eval_polys(cudaStream_t s, const uint4* coeff, uint64_t pitch, uint32_t ncols, uint32_t log_n, const uint4* pw,
                uint32_t npoints, uint4* scratch, uint4* out) {
     uint32_t nblocks = log_n > kEvalChunkLog ? 1u << (log_n - kEvalChunkLog) : 1;
     dim3 grid(nblocks, ncols);
     {
-        LaunchScope ls(s, K_EVAL_POLYS, ((uint64_t)ncols << log_n) * 16);
-        eval_partial_kernel<<<grid, kEvalThreads, 0, s>>>(coeff, pitch, log_n, fe_make(y[0][0], y[0][1]),
-                                                          fe_make(y[1][0], y[1][1]), npoints, scratch);
+        LaunchScope ls(s, K_EVAL_POLYS, ((uint64_t)(ncols + npoints) << log_n) * 16);
+        if (npoints == 2)
+            eval_partial_kernel<2><<<grid, kEvalThreads, 0, s>>>(coeff, pitch, log_n, pw, scratch);
+        else
+            eval_partial_kernel<1><<<grid, kEvalThreads, 0, s>>>(coeff, pitch, log_n, pw, scratch);
     }
     EZK_CUDA(cudaGetLastError());
     uint32_t nout = ncols * npoints;

@@ -12,9 +12,13 @@
 
 namespace ezk {
 
-// out[(c * npoints + k)] = sum_m coeff[c][m] * y_k^m   for c < ncols, k < npoints (npoints <= 2).
+// pw[k][m] = y_k^m, m < n = 2^log_n, k < npoints (npoints <= 2; pitch n)
+int power_table(cudaStream_t s, uint32_t log_n, const uint64_t y[2][2], uint32_t npoints, uint4* pw);
+
+// out[(c * npoints + k)] = sum_m coeff[c][m] * y_k^m   for c < ncols, k < npoints (npoints <= 2), as dot products with
+// the power table `pw` of power_table() (independent terms instead of a Horner chain).
 // scratch: ncols * npoints * blocks_per_col elements, blocks_per_col = max(1, n / 16384).
-int eval_polys(cudaStream_t s, const uint4* coeff, uint64_t pitch, uint32_t ncols, uint32_t log_n, const uint64_t y[2][2],
+int eval_polys(cudaStream_t s, const uint4* coeff, uint64_t pitch, uint32_t ncols, uint32_t log_n, const uint4* pw,
                uint32_t npoints, uint4* scratch, uint4* out);
 
 // pq[0][m] = sum_{c<28} tc[c] * tcoeff[c][m];  pq[1][m] = sum_{j<7} cc[j] * ccoeff[j][m]   (pq pitch = n)

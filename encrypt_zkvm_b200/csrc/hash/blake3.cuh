@@ -26,6 +26,9 @@ namespace dev {
 
 __device__ __forceinline__ uint32_t b3_rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 
+// Measured and kept out: issuing the additions as integer multiply-adds (x * 1 + y with the 1 read from constant
+// memory, so that they run on the FMA pipe: 8 ALU + 6 FMA instructions per G instead of 10 + 2) leaves the hash
+// kernels' time unchanged on the B200 (2.70 -> 2.68 ms per 2^20 proof) although the ALU pipe reads 96 % busy.
 #define B3_G(a, b, c, d, mx, my)   \
     a = a + b + (mx);              \
     d = __byte_perm(d ^ a, 0, 0x1032); /* rotr 16 */ \

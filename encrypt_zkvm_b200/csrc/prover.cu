@@ -144,6 +144,7 @@ GpuProver::~GpuProver() {
     cudaStreamDestroy(aux_stream_);
     cudaFree(d_flag_);
     cudaFree(d_params_);
+    cudaFree(d_bden_);
     cudaFreeHost(pinned_);
     cudaFree(arena_.base);
     ntt_tables_free(tables_);
@@ -308,16 +309,33 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         }
     }
     mark();
-    // the divisor inverses of the boundary constraints depend on n only: compute them on the auxiliary stream while
-    // the (latency-bound) Merkle tree of the trace commitment is built and its root travels to the host
+    // the divisor inverses of the boundary constraints depend on n (and the row shard) only: cached across proofs of
+    // the same length; the first proof computes them on the auxiliary stream while the (latency-bound) Merkle tree
+    // of the trace commitment is built and its root travels to the host
     const Fp g_last = pow(g, n - 2), g_last2 = pow(g, n - 1);
+    const uint4* d_bden = d_invden;
     {
+        const uint64_t key = ((uint64_t)log_n << 16) | ((uint64_t)sh.world_log << 8) | sh.rank | (1ull << 40);
+        bool have = d_bden_ && bden_key_ == key;
+        if (!have) {
+            if (d_bden_) cudaFree(d_bden_);  // no proof is in flight: prove() ends with a stream synchronisation
+            d_bden_ = nullptr, bden_key_ = 0;
+            if (cudaMalloc(&d_bden_, L_local * sizeof(uint4)) != cudaSuccess) {
+                cudaGetLastError();
+                d_bden_ = nullptr;
+            }
+        }
+        uint4* target = d_bden_ ? d_bden_ : d_invden;
         EZK_CUDA(cudaEventRecord(aux_ev_[0], stream_));
         EZK_CUDA(cudaStreamWaitEvent(aux_stream_, aux_ev_[0], 0));
-        uint64_t a[2], b[2];
-        put(a, Fp(1)), put(b, g_last);
-        domain_pair_inverse(aux_stream_, tables_.root_fwd, tables_.root_inv, log_L, a, b, d_invden, sh);
+        if (!have) {
+            uint64_t a[2], b[2];
+            put(a, Fp(1)), put(b, g_last);
+            domain_pair_inverse(aux_stream_, tables_.root_fwd, tables_.root_inv, log_L, a, b, target, sh);
+            if (d_bden_) bden_key_ = key;
+        }
         EZK_CUDA(cudaEventRecord(aux_ev_[1], aux_stream_));
+        d_bden = target;
     }
     commit_rows(d_tlde, kWidth, d_tnodes);
     last_.trace_root = root_of(d_tnodes);
@@ -376,7 +394,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         for (uint32_t k = 0; k < 128 * kPeriodic; k++) put(hp.ptable[k], ptable_[k]);
         h2d(d_params_, &hp, sizeof(hp));
         EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[1], 0));
-        evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_invden, sharded ? d_pack : d_combined, sh);
+        evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_bden, sharded ? d_pack : d_combined, sh);
         if (sharded) share_rows(1, d_combined);
     }
     mark();
@@ -425,8 +443,10 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
             domain_pair_inverse(aux_stream_, tables_.root_fwd, tables_.root_inv, log_L, a, b, d_invden, sh);
             EZK_CUDA(cudaEventRecord(aux_ev_[3], aux_stream_));
         }
-        eval_polys(stream_, d_tcoef, n, kWidth, log_n, y, 2, d_scratch, d_ood);
-        eval_polys(stream_, d_ccoef, n, kCompCols, log_n, y, 1, d_scratch + (size_t)2 * kWidth * eval_blocks, d_ood + 2 * kWidth);
+        // powers of the two points once (d_pq is free until the DEEP combination), then 63 dot products
+        power_table(stream_, log_n, y, 2, d_pq);
+        eval_polys(stream_, d_tcoef, n, kWidth, log_n, d_pq, 2, d_scratch, d_ood);
+        eval_polys(stream_, d_ccoef, n, kCompCols, log_n, d_pq, 1, d_scratch + (size_t)2 * kWidth * eval_blocks, d_ood + 2 * kWidth);
         std::vector<Fp> host(2 * kWidth + kCompCols);
         d2h(host.data(), d_ood, host.size() * 16);
         std::copy(host.begin(), host.begin() + 2 * kWidth, ood_trace.begin());

@@ -82,6 +82,11 @@ private:
     float stage_ms_[8] = {0};
     std::vector<Fp> ptable_;        // periodic columns over the LDE domain, cached per trace length
     uint32_t ptable_log_n_ = 0;
+    // 1 / ((x - 1)(x - g^(n-2))) over this rank's LDE rows: the boundary-constraint divisors depend on the trace
+    // length (and the row shard) only, so they are kept across proofs (L * 16 bytes; recomputed per proof in the
+    // arena when the allocation fails)
+    uint4* d_bden_ = nullptr;
+    uint64_t bden_key_ = 0;
 
     // state of the last proof (device pointers into the arena + host copies), for ezk_prover_artifact
     struct Last {
