@@ -33,12 +33,43 @@ __global__ void __launch_bounds__(kEvalThreads) power_table_kernel(uint32_t log_
     }
 }
 
+// acc[k] += sum over this thread's coefficients of a[m] * pw[k][m]; U coefficients per step, all their loads issued
+// before the first product (the kernel is otherwise bound by the latency of its loads)
+template <int NP, class AR>
+__device__ __forceinline__ bool eval_thread(const uint4* __restrict__ col, const uint4* __restrict__ pw, uint64_t n,
+                                            uint64_t chunk, uint32_t t, uint32_t T, fe (&acc)[NP]) {
+    AR ar;
+#pragma unroll
+    for (int k = 0; k < NP; k++) acc[k] = fe_zero();
+    constexpr int U = NP == 2 ? 2 : 4;
+    uint64_t m = t;
+    for (; m + (U - 1) * T < chunk; m += U * T) {
+        fe a[U], w[NP][U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            a[u] = fe_ldg(col + m + u * T);
+#pragma unroll
+            for (int k = 0; k < NP; k++) w[k][u] = fe_ldg(pw + (uint64_t)k * n + m + u * T);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int k = 0; k < NP; k++) acc[k] = ar.add(acc[k], ar.mul(a[u], w[k][u]));
+    }
+    for (; m < chunk; m += T) {
+        const fe a = fe_ldg(col + m);
+#pragma unroll
+        for (int k = 0; k < NP; k++) acc[k] = ar.add(acc[k], ar.mul(a, fe_ldg(pw + (uint64_t)k * n + m)));
+    }
+    return ar.tainted();
+}
+
 // block (bx, col): partial dot products of coefficients [bx*chunk, (bx+1)*chunk) with the power tables of up to 2
 // points.  Every term is independent (no Horner chain), so the products of a thread overlap.
 template <int NP>
-__global__ void __launch_bounds__(kEvalThreads) eval_partial_kernel(const uint4* __restrict__ coeff, uint64_t pitch,
-                                                                   uint32_t log_n, const uint4* __restrict__ pw,
-                                                                   uint4* __restrict__ scratch) {
+__global__ void __launch_bounds__(kEvalThreads, 4) eval_partial_kernel(const uint4* __restrict__ coeff, uint64_t pitch,
+                                                                      uint32_t log_n, const uint4* __restrict__ pw,
+                                                                      uint4* __restrict__ scratch) {
     __shared__ uint4 red[NP][kEvalThreads];
     const uint64_t n = 1ull << log_n;
     const uint64_t chunk = n < (1ull << kEvalChunkLog) ? n : (1ull << kEvalChunkLog);
@@ -46,14 +77,8 @@ __global__ void __launch_bounds__(kEvalThreads) eval_partial_kernel(const uint4*
     const uint4* col = coeff + (uint64_t)blockIdx.y * pitch + base;
     const uint32_t T = blockDim.x, t = threadIdx.x;
     fe acc[NP];
-#pragma unroll
-    for (int k = 0; k < NP; k++) acc[k] = fe_zero();
-#pragma unroll 4
-    for (uint64_t m = t; m < chunk; m += T) {
-        const fe a = fe_ldg(col + m);
-#pragma unroll
-        for (int k = 0; k < NP; k++) acc[k] = fe_add(acc[k], fe_mul(a, fe_ldg(pw + (uint64_t)k * n + base + m)));
-    }
+    if (eval_thread<NP, Arith<true>>(col, pw + base, n, chunk, t, T, acc))
+        eval_thread<NP, Arith<false>>(col, pw + base, n, chunk, t, T, acc);  // a rare tail of the fast arithmetic: redo exactly
 #pragma unroll
     for (int k = 0; k < NP; k++) fe_store(&red[k][t], acc[k]);
     __syncthreads();

@@ -343,8 +343,13 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_strided_pass(StridedArgs a)
     P.lo0 = (blockIdx.x % tiles_per_hi) * lanes;
     const uint64_t hi = blockIdx.x / tiles_per_hi;
     P.base = P.lo0 + (hi << (a.log_stride + a.log_s));
-    const uint32_t col = blockIdx.y;
+    uint32_t col = blockIdx.y;
     if (a.coset_first) {
+        // coset-major launch order: the CTAs of all columns of one coset run back to back, so that coset's slice of
+        // the inter-pass twiddle table (N entries) is read from DRAM once and then served by L2 for the other columns
+        const uint32_t real_cols = gridDim.y >> a.cs_log;
+        const uint32_t ci = blockIdx.y / real_cols;
+        col = ((blockIdx.y - ci * real_cols) << a.cs_log) | ci;
         P.coset = a.cs_base + a.cs_step * (col & ((1u << a.cs_log) - 1));
         P.src = a.src + (uint64_t)(col >> a.cs_log) * a.src_pitch;
     } else {

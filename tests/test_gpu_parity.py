@@ -170,6 +170,22 @@ def test_invalid_trace_is_rejected(gpu_prover_factory):
         assert ei.value.code in (-3, -4)
 
 
+def test_prover_state_survives_other_trace_lengths(gpu_prover_factory):
+    """The prover keeps per-length tables across proofs (periodic columns, boundary divisors, twiddle tables): a call
+    with another trace length in between — here one that is rejected — must not leak into the next proof."""
+    ezk = gpu_prover_factory
+    a, b = synthetic(2, 10), synthetic(1, 11)
+    with ezk.ExecutionProver(ezk.ProofOptions(), a.program_hash, a.outputs, ezk.ServerKey()) as p:
+        first = p.prove(a.trace).to_bytes()
+        with pytest.raises(ezk.ProverError):
+            p.prove(b.trace)  # other length, and not a trace of this program
+        second = p.prove(a.trace).to_bytes()
+        with pytest.raises(ezk.ProverError):
+            p.prove(b.trace[:, :512])
+        third = p.prove(a.trace).to_bytes()
+    assert first == second == third
+
+
 def test_argument_errors(gpu_prover_factory):
     ezk = gpu_prover_factory
     case = synthetic(1, 7)
