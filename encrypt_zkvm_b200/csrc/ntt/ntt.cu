@@ -381,6 +381,7 @@ struct FinalArgs {
     const uint4* roots;
     const uint4* tw;
     const uint4* off_tab;
+    const uint4* scale_tab;  // optional: scale_tab[m] = cvec[0] * o^m (see NttTables::ScaleTable)
     NttScale scale;
 };
 
@@ -434,6 +435,7 @@ struct FinalPass {
     __device__ __forceinline__ fe finish(A& ar, const Out& o, int p, fe v) const {
         if (a->mode == 0 && a->scale.enabled) {
             const uint64_t out = o.index + p * o.step;
+            if (a->scale_tab) return ar.mul(v, fe_ldg(a->scale_tab + out));
             const uint32_t ci = (uint32_t)(out >> a->scale.chunk_shift);
             fe c = fe_make(a->scale.cvec[ci][0], a->scale.cvec[ci][1]);
             if (a->scale.use_offset) c = ar.mul(c, tab_pow(ar, a->off_tab, (uint32_t)out));
@@ -611,6 +613,36 @@ const uint4* pass_table(const NttTables& t, cudaStream_t s, bool inverse, bool c
     return d;
 }
 
+__global__ void build_scale_table_kernel(const uint4* __restrict__ off_tab, fe c, uint64_t n, uint4* __restrict__ out) {
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n) fe_store(out + m, fe_mul(c, fe_tab_pow(off_tab, (uint32_t)m)));
+}
+
+// S[m] = c * o^m for m < 2^log_n, cached for the latest (length, constant); nullptr when it cannot be used
+const uint4* scale_table(const NttTables& t, cudaStream_t s, uint32_t log_n, const NttScale& sc) {
+    NttTables::ScaleTable* st = t.scale_table;
+    if (!st || sc.use_offset != 1 || sc.chunk_shift < 32 || log_n > 27 || (16ull << log_n) > t.big_table_limit_bytes) return nullptr;
+    if (st->d && st->log_n == log_n && st->c[0] == sc.cvec[0][0] && st->c[1] == sc.cvec[0][1]) return st->d;
+    if (st->d) {
+        EZK_CUDA(cudaStreamSynchronize(s));  // the old table may still be read by a kernel in flight on this stream
+        cudaFree(st->d);
+        st->d = nullptr;
+    }
+    if (cudaMalloc(&st->d, 16ull << log_n) != cudaSuccess) {
+        cudaGetLastError();
+        st->d = nullptr;
+        return nullptr;
+    }
+    const uint64_t n = 1ull << log_n;
+    {
+        LaunchScope ls(s, K_NTT_FINAL, n * 16);
+        build_scale_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t.off_fwd, fe_make(sc.cvec[0][0], sc.cvec[0][1]), n, st->d);
+    }
+    EZK_CUDA(cudaGetLastError());
+    st->log_n = log_n, st->c[0] = sc.cvec[0][0], st->c[1] = sc.cvec[0][1];
+    return st->d;
+}
+
 // strided passes p..2 over `ncols` arrays of n elements: the first pass reads `first_src` and writes `buf`,
 // later passes run in place in `buf`.  With `coset` the first pass reads coefficient column y/8 and applies the
 // coset factor w_L^(c*m), c = y%8 (LDE).
@@ -703,6 +735,7 @@ void ntt_tables_init(NttTables& t) {
     }
     EZK_CUDA(cudaMemcpyToSymbol(c_w8pre, w8, sizeof(w8)));
     t.big_tables = new std::map<uint64_t, uint4*>();
+    t.scale_table = new NttTables::ScaleTable();
     if (const char* e = getenv("EZK_NTT_BIG_TABLE_MB")) t.big_table_limit_bytes = (uint64_t)atoll(e) << 20;
     const char* env = getenv("EZK_NTT_TILE_LOG");
     if (env) {
@@ -717,6 +750,10 @@ void ntt_tables_free(NttTables& t) {
     if (t.big_tables) {
         for (auto& kv : *t.big_tables) cudaFree(kv.second);
         delete t.big_tables;
+    }
+    if (t.scale_table) {
+        cudaFree(t.scale_table->d);
+        delete t.scale_table;
     }
     t = NttTables{};
 }
@@ -759,6 +796,7 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
     a.tw = inverse ? t.tw_inv : t.tw_fwd;
     a.off_tab = off_tab;
     a.scale = sc;
+    a.scale_tab = scale ? scale_table(t, s, log_n, sc) : nullptr;
     uint64_t runs = 1ull << (log_n - pl.log_d[0]);
     dim3 grid((unsigned)(pl.passes >= 2 ? runs >> a.lanes_log : 1), ncols);
     {

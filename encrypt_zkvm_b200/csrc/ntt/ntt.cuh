@@ -22,6 +22,14 @@ struct NttTables {
     std::map<uint64_t, uint4*>* big_tables = nullptr;
     uint64_t big_table_limit_bytes = 1ull << 30;
     int max_tile_log = 10;      // largest single-CTA transform (2^10 points x 4 lanes, 2^9 x 8 lanes)
+    // output scaling of the trace interpolation as one table, S[m] = c * o^m (c = 1/n), kept for the latest length:
+    // one load + one product per coefficient instead of a two-level power lookup + up to three products
+    struct ScaleTable {
+        uint4* d = nullptr;
+        uint32_t log_n = 0;
+        uint64_t c[2] = {0, 0};
+    };
+    ScaleTable* scale_table = nullptr;
 };
 
 void ntt_tables_init(NttTables& t);
