@@ -61,8 +61,11 @@ __device__ __forceinline__ fe fe_fix_rare(fe s, uint32_t ov) {
     return s;
 }
 
-// a + b - [carry] * M: canonical unless the result lies in [M, 2^128), which needs limb 3 = all ones
-__device__ __forceinline__ fe fe_add_raw(fe a, fe b) {
+// a + b - [carry] * M: canonical unless the result lies in [M, 2^128), which needs limb 3 = all ones.
+// Two encodings of the same operation (ptxas output: 12 and 10 instructions).  The masked one keeps everything in
+// general registers; the predicated one turns the carry into the guard of four predicated additions.  Which one is
+// faster depends on the kernel (predicate registers are scarce): see Arith below.
+__device__ __forceinline__ fe fe_add_raw_masked(fe a, fe b) {
     fe s;
     uint32_t c;
     asm("add.cc.u32 %0, %5, %9;\n\t"
@@ -82,10 +85,34 @@ __device__ __forceinline__ fe fe_add_raw(fe a, fe b) {
         : "r"(m0), "r"(m1));
     return s;
 }
+__device__ __forceinline__ fe fe_add_raw(fe a, fe b) {
+    fe s;
+    // carry out of 2^128: s - M = s + K - 2^128, applied by four additions predicated on the carry (about half of
+    // all additions take it)
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 c;\n\t"
+        "add.cc.u32 %0, %4, %8;\n\t"
+        "addc.cc.u32 %1, %5, %9;\n\t"
+        "addc.cc.u32 %2, %6, %10;\n\t"
+        "addc.cc.u32 %3, %7, %11;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "setp.ne.u32 p, c, 0;\n\t"
+        "@p add.cc.u32 %0, %0, 0xFFFFFFFF;\n\t"
+        "@p addc.cc.u32 %1, %1, 0x2CFF;\n\t"
+        "@p addc.cc.u32 %2, %2, 0;\n\t"
+        "@p addc.u32 %3, %3, 0;\n\t"
+        "}"
+        : "=&r"(s.a0), "=&r"(s.a1), "=&r"(s.a2), "=&r"(s.a3)
+        : "r"(a.a0), "r"(a.a1), "r"(a.a2), "r"(a.a3), "r"(b.a0), "r"(b.a1), "r"(b.a2), "r"(b.a3));
+    return s;
+}
 
 // r = a + b (mod M), canonical inputs -> canonical output
 __device__ __forceinline__ fe fe_add(fe a, fe b) {
-    fe s = fe_add_raw(a, b);
+    // the exact functions sit on rarely taken paths next to the hot loops; the register-only encoding keeps the
+    // out-of-line redo functions from adding spills around their call sites
+    fe s = fe_add_raw_masked(a, b);
     if (s.a3 == 0xFFFFFFFFu) s = fe_fix_rare(s, 0);  // only values >= 2^128 - 2^96 can still be >= M
     return s;
 }
@@ -96,6 +123,11 @@ __device__ __forceinline__ fe fe_add(fe a, fe b) {
 // free of branches lets ptxas interleave the independent carry chains of neighbouring butterflies.
 __device__ __forceinline__ fe fe_add_flag(fe a, fe b, uint32_t& rare) {
     fe s = fe_add_raw(a, b);
+    rare = max(rare, s.a3);
+    return s;
+}
+__device__ __forceinline__ fe fe_add_flag_masked(fe a, fe b, uint32_t& rare) {
+    fe s = fe_add_raw_masked(a, b);
     rare = max(rare, s.a3);
     return s;
 }
@@ -144,6 +176,29 @@ __device__ __forceinline__ fe fe_fold_top_raw(fe s, uint32_t p0, uint32_t p1, ui
         : "r"(p0), "r"(p1));
     return s;
 }
+
+// The same fold for the flagged (branch-free) products: no carry capture.  top * (11520 * 2^32 - 1) < 2^92, so the
+// sum can only wrap past 2^128 when limb 3 of `s` was all ones BEFORE the fold; the caller flags on that limb
+// before and after (one three-input max) instead of materialising the carry.
+__device__ __forceinline__ fe fe_fold_top_nowrap(fe s, uint32_t p0, uint32_t p1) {
+    asm("{\n\t"
+        ".reg .u32 v1, v2, q0, q1, q2;\n\t"
+        "mul.lo.u32 v1, %4, 11520;\n\t"
+        "mul.hi.u32 v2, %4, 11520;\n\t"
+        "mad.lo.u32 v2, %5, 11520, v2;\n\t"
+        "sub.cc.u32 q0, 0, %4;\n\t"
+        "subc.cc.u32 q1, v1, %5;\n\t"
+        "subc.u32 q2, v2, 0;\n\t"
+        "add.cc.u32 %0, %0, q0;\n\t"
+        "addc.cc.u32 %1, %1, q1;\n\t"
+        "addc.cc.u32 %2, %2, q2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "}"
+        : "+r"(s.a0), "+r"(s.a1), "+r"(s.a2), "+r"(s.a3)
+        : "r"(p0), "r"(p1));
+    return s;
+}
+__device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return max(a, max(b, c)); }
 
 // ... -> canonical element
 __device__ __forceinline__ fe fe_fold_top(fe s, uint32_t p0, uint32_t p1) {
@@ -252,15 +307,30 @@ __device__ __forceinline__ fe fe_mul(fe a, fe b) {
     return fe_reduce256(r);
 }
 
+// last fold of a flagged product.  NOWRAP: flag on limb 3 before and after the fold (58 instructions per product);
+// otherwise capture the fold's carry (60 instructions, one register less alive across the fold).
+template <bool NOWRAP>
+__device__ __forceinline__ fe fe_fold_top_flag(fe s, uint32_t p0, uint32_t p1, uint32_t& rare) {
+    if (NOWRAP) {
+        const uint32_t before = s.a3;
+        s = fe_fold_top_nowrap(s, p0, p1);
+        rare = umax3(rare, before, s.a3);
+    } else {
+        uint32_t ov;
+        s = fe_fold_top_raw(s, p0, p1, ov);
+        rare = max(rare, max(s.a3, 0u - ov));
+    }
+    return s;
+}
+
 // branch-free product, see fe_add_flag
+template <bool NOWRAP = true>
 __device__ __forceinline__ fe fe_mul_flag(fe a, fe b, uint32_t& rare) {
-    uint32_t r[8], p0, p1, ov;
+    uint32_t r[8], p0, p1;
     fe s;
     fe_mul256(a, b, r);
     fe_reduce256_first(r, s, p0, p1);
-    s = fe_fold_top_raw(s, p0, p1, ov);
-    rare = max(rare, max(s.a3, 0u - ov));
-    return s;
+    return fe_fold_top_flag<NOWRAP>(s, p0, p1, rare);
 }
 
 __device__ __forceinline__ fe fe_sqr(fe a) { return fe_mul(a, a); }
@@ -359,13 +429,12 @@ __device__ __forceinline__ fe fe_mul_pre(const fe& x, const fe_pre& W) {
     fe_mul_pre_raw(x, W, s, p0, p1);
     return fe_fold_top(s, p0, p1);
 }
+template <bool NOWRAP = true>
 __device__ __forceinline__ fe fe_mul_pre_flag(const fe& x, const fe_pre& W, uint32_t& rare) {
     fe s;
-    uint32_t p0, p1, ov;
+    uint32_t p0, p1;
     fe_mul_pre_raw(x, W, s, p0, p1);
-    s = fe_fold_top_raw(s, p0, p1, ov);
-    rare = max(rare, max(s.a3, 0u - ov));
-    return s;
+    return fe_fold_top_flag<NOWRAP>(s, p0, p1, rare);
 }
 
 // branch-free a * small, see fe_add_flag
@@ -373,13 +442,21 @@ __device__ __forceinline__ fe fe_mul_small_flag(fe a, uint32_t k, uint32_t& rare
 
 // Arithmetic policy of a straight-line block.  FAST: branch-free operations that only record their rare tails in
 // `rare`; the caller checks tainted() once and recomputes the block with the exact policy (a few times per proof).
-template <bool FAST>
+// LEAN selects the shorter encodings (predicated additions, products flagged without a carry capture: -2 instructions
+// each).  Measured per kernel on the B200 at 2^20: constraint kernel 5.46 -> 4.49 ms, final NTT pass 7.08 -> 6.90 ms,
+// but the strided NTT pass 10.05 -> 11.11 ms (it is the one kernel that loses: more values alive per thread), so that
+// pass keeps the register-only encodings (LEAN = false).
+template <bool FAST, bool LEAN = true>
 struct Arith {
     uint32_t rare = 0;
-    __device__ __forceinline__ fe add(fe a, fe b) { return FAST ? fe_add_flag(a, b, rare) : fe_add(a, b); }
+    __device__ __forceinline__ fe add(fe a, fe b) {
+        return FAST ? (LEAN ? fe_add_flag(a, b, rare) : fe_add_flag_masked(a, b, rare)) : fe_add(a, b);
+    }
     __device__ __forceinline__ fe sub(fe a, fe b) { return fe_sub(a, b); }
-    __device__ __forceinline__ fe mul(fe a, fe b) { return FAST ? fe_mul_flag(a, b, rare) : fe_mul(a, b); }
-    __device__ __forceinline__ fe mul_pre(const fe& a, const fe_pre& w) { return FAST ? fe_mul_pre_flag(a, w, rare) : fe_mul_pre(a, w); }
+    __device__ __forceinline__ fe mul(fe a, fe b) { return FAST ? fe_mul_flag<LEAN>(a, b, rare) : fe_mul(a, b); }
+    __device__ __forceinline__ fe mul_pre(const fe& a, const fe_pre& w) {
+        return FAST ? fe_mul_pre_flag<LEAN>(a, w, rare) : fe_mul_pre(a, w);
+    }
     __device__ __forceinline__ fe sqr(fe a) { return mul(a, a); }
     __device__ __forceinline__ fe cube(fe a) { return mul(mul(a, a), a); }
     __device__ __forceinline__ fe mul_small(fe a, uint32_t k) { return FAST ? fe_mul_small_flag(a, k, rare) : fe_mul_small(a, k); }
@@ -396,11 +473,9 @@ struct ArithLockstep : Arith<true> {
 
 __device__ __forceinline__ fe fe_mul_small_flag(fe a, uint32_t k, uint32_t& rare) {
     fe s;
-    uint32_t p0, ov;
+    uint32_t p0;
     fe_mul_small_raw(a, k, s, p0);
-    s = fe_fold_top_raw(s, p0, 0, ov);
-    rare = max(rare, max(s.a3, 0u - ov));
-    return s;
+    return fe_fold_top_flag<true>(s, p0, 0, rare);
 }
 
 __device__ __forceinline__ fe fe_pow(fe b, uint64_t e) {
