@@ -307,14 +307,19 @@ __device__ __forceinline__ fe fe_mul(fe a, fe b) {
     return fe_reduce256(r);
 }
 
-// last fold of a flagged product.  NOWRAP: flag on limb 3 before and after the fold (58 instructions per product);
-// otherwise capture the fold's carry (60 instructions, one register less alive across the fold).
-template <bool NOWRAP>
+// last fold of a flagged product.  MODE 1: flag on limb 3 before and after the fold with one three-input max (58
+// instructions per product, one more register alive across the fold); MODE 2: the same test as two separate max
+// operations (59, no extra register); MODE 0: capture the fold's carry instead (60).
+template <int MODE>
 __device__ __forceinline__ fe fe_fold_top_flag(fe s, uint32_t p0, uint32_t p1, uint32_t& rare) {
-    if (NOWRAP) {
+    if (MODE == 1) {
         const uint32_t before = s.a3;
         s = fe_fold_top_nowrap(s, p0, p1);
         rare = umax3(rare, before, s.a3);
+    } else if (MODE == 2) {
+        rare = max(rare, s.a3);
+        s = fe_fold_top_nowrap(s, p0, p1);
+        rare = max(rare, s.a3);
     } else {
         uint32_t ov;
         s = fe_fold_top_raw(s, p0, p1, ov);
@@ -324,13 +329,13 @@ __device__ __forceinline__ fe fe_fold_top_flag(fe s, uint32_t p0, uint32_t p1, u
 }
 
 // branch-free product, see fe_add_flag
-template <bool NOWRAP = true>
+template <int MODE = 1>
 __device__ __forceinline__ fe fe_mul_flag(fe a, fe b, uint32_t& rare) {
     uint32_t r[8], p0, p1;
     fe s;
     fe_mul256(a, b, r);
     fe_reduce256_first(r, s, p0, p1);
-    return fe_fold_top_flag<NOWRAP>(s, p0, p1, rare);
+    return fe_fold_top_flag<MODE>(s, p0, p1, rare);
 }
 
 __device__ __forceinline__ fe fe_sqr(fe a) { return fe_mul(a, a); }
@@ -429,12 +434,12 @@ __device__ __forceinline__ fe fe_mul_pre(const fe& x, const fe_pre& W) {
     fe_mul_pre_raw(x, W, s, p0, p1);
     return fe_fold_top(s, p0, p1);
 }
-template <bool NOWRAP = true>
+template <int MODE = 1>
 __device__ __forceinline__ fe fe_mul_pre_flag(const fe& x, const fe_pre& W, uint32_t& rare) {
     fe s;
     uint32_t p0, p1;
     fe_mul_pre_raw(x, W, s, p0, p1);
-    return fe_fold_top_flag<NOWRAP>(s, p0, p1, rare);
+    return fe_fold_top_flag<MODE>(s, p0, p1, rare);
 }
 
 // branch-free a * small, see fe_add_flag
@@ -446,16 +451,16 @@ __device__ __forceinline__ fe fe_mul_small_flag(fe a, uint32_t k, uint32_t& rare
 // each).  Measured per kernel on the B200 at 2^20: constraint kernel 5.46 -> 4.49 ms, final NTT pass 7.08 -> 6.90 ms,
 // but the strided NTT pass 10.05 -> 11.11 ms (it is the one kernel that loses: more values alive per thread), so that
 // pass keeps the register-only encodings (LEAN = false).
-template <bool FAST, bool LEAN = true>
+template <bool FAST, bool LEAN = true, int LEAN_MUL = LEAN ? 1 : 0>
 struct Arith {
     uint32_t rare = 0;
     __device__ __forceinline__ fe add(fe a, fe b) {
         return FAST ? (LEAN ? fe_add_flag(a, b, rare) : fe_add_flag_masked(a, b, rare)) : fe_add(a, b);
     }
     __device__ __forceinline__ fe sub(fe a, fe b) { return fe_sub(a, b); }
-    __device__ __forceinline__ fe mul(fe a, fe b) { return FAST ? fe_mul_flag<LEAN>(a, b, rare) : fe_mul(a, b); }
+    __device__ __forceinline__ fe mul(fe a, fe b) { return FAST ? fe_mul_flag<LEAN_MUL>(a, b, rare) : fe_mul(a, b); }
     __device__ __forceinline__ fe mul_pre(const fe& a, const fe_pre& w) {
-        return FAST ? fe_mul_pre_flag<LEAN>(a, w, rare) : fe_mul_pre(a, w);
+        return FAST ? fe_mul_pre_flag<LEAN_MUL>(a, w, rare) : fe_mul_pre(a, w);
     }
     __device__ __forceinline__ fe sqr(fe a) { return mul(a, a); }
     __device__ __forceinline__ fe cube(fe a) { return mul(mul(a, a), a); }
@@ -475,7 +480,7 @@ __device__ __forceinline__ fe fe_mul_small_flag(fe a, uint32_t k, uint32_t& rare
     fe s;
     uint32_t p0;
     fe_mul_small_raw(a, k, s, p0);
-    return fe_fold_top_flag<true>(s, p0, 0, rare);
+    return fe_fold_top_flag<1>(s, p0, 0, rare);
 }
 
 __device__ __forceinline__ fe fe_pow(fe b, uint64_t e) {

@@ -181,7 +181,7 @@ struct StepCtx {
 template <bool FAST, int INV, class Pass>
 __device__ __forceinline__ bool group_compute(const Pass& P, const uint4* tile, const StepCtx& c, uint32_t lane, uint32_t i0,
                                               uint32_t q, uint32_t jg, fe (&x)[8]) {
-    Arith<FAST, Pass::kLean> ar;
+    Arith<FAST, Pass::kLean, Pass::kLeanMul> ar;
     const uint32_t sh = c.log_cur - 3;
     // slot p of the group sits at a fixed stride from slot 0: one base address per group, p * step per slot
     if (c.first) {
@@ -281,7 +281,11 @@ struct StridedArgs {
 };
 
 struct StridedPass {
-    static constexpr bool kLean = false;  // arithmetic encodings, see Arith in f128.cuh
+    // arithmetic encodings, see Arith in f128.cuh: this pass (latency-bound on its strided loads and table reads, and
+    // at the register limit) gains nothing from the shorter ones (10.04 vs 10.02 ms) and loses with the spills the
+    // carry-free product flag brings (10.43 ms)
+    static constexpr bool kLean = false;
+    static constexpr int kLeanMul = 0;
     const uint4* src;
     uint4* dst;
     const uint4* roots;
@@ -388,6 +392,7 @@ struct FinalArgs {
 
 struct FinalPass {
     static constexpr bool kLean = true;
+    static constexpr int kLeanMul = 1;
     const FinalArgs* a;
     const uint4* src;   // column base (mode 0, 2) or coset-0 base of this column group (mode 1)
     uint4* dst;
