@@ -70,10 +70,15 @@ struct LdeFrame {
 };
 
 struct SumSink {
+    static constexpr bool kGrouped = true;  // only sum_j tcoef_j * r_j is wanted: see eval_transition
     const ConstraintParams* __restrict__ p;
     fe acc;
     template <class A>
-    __device__ __forceinline__ void put(A& ar, int j, fe v) { acc = ar.add(acc, ar.mul_pre(v, ld_pre(p->tcoef_pre[j]))); }
+    __device__ __forceinline__ fe scaled(A& ar, int j, fe v) { return ar.mul_pre(v, ld_pre(p->tcoef_pre[j])); }
+    template <class A>
+    __device__ __forceinline__ void add(A& ar, fe v) { acc = ar.add(acc, v); }
+    template <class A>
+    __device__ __forceinline__ void put(A& ar, int j, fe v) { acc = ar.add(acc, scaled(ar, j, v)); }
 };
 
 // combined evaluation of one LDE row; returns true when the FAST arithmetic hit a rare tail (value unusable)
@@ -105,7 +110,8 @@ __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, 
     for (int k = 0; k < 12; k++) s0 = ar.add(s0, ar.mul_pre(f.cur(p->bcol[k]), ld_pre(p->bcoef_pre[k])));
     ar.checkpoint();
 #pragma unroll
-    for (int k = 12; k < 22; k++) s1 = ar.add(s1, ar.mul_pre(ar.sub(f.cur(p->bcol[k]), ld2(p->bval[k])), ld_pre(p->bcoef_pre[k])));
+    for (int k = 12; k < 22; k++) s1 = ar.add(s1, ar.mul_pre(f.cur(p->bcol[k]), ld_pre(p->bcoef_pre[k])));
+    s1 = ar.sub(s1, ld2(p->bsum1));  // sum bcoef_k (cur_k - val_k) = sum bcoef_k cur_k - sum bcoef_k val_k
     ar.checkpoint();
     // B0/(x-1) + B1/(x-a) = (B0 (x-a) + B1 (x-1)) / ((x-1)(x-a))
     const fe num = ar.add(ar.mul(s0, ar.sub(x, a)), ar.mul(s1, ar.sub(x, fe_one())));
@@ -144,7 +150,12 @@ struct ArrayFrame {
     __device__ __forceinline__ fe nxt(int k) const { return fe_load(n + k); }
 };
 struct StoreSink {
+    static constexpr bool kGrouped = false;  // every constraint value on its own
     uint4* out;
+    template <class A>
+    __device__ __forceinline__ fe scaled(A&, int, fe v) { return v; }
+    template <class A>
+    __device__ __forceinline__ void add(A&, fe) {}
     template <class A>
     __device__ __forceinline__ void put(A&, int j, fe v) { fe_store(out + j, v); }
 };

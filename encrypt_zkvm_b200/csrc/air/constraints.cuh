@@ -12,6 +12,7 @@ struct ConstraintParams {  // device-resident, rebuilt for every proof (depends 
     uint64_t tcoef[20][2];     // transition composition coefficients
     uint64_t bcoef[22][2];     // boundary composition coefficients, in sorted-assertion order
     uint64_t bval[22][2];      // asserted values (12 zeros for step 0, then 10 values for step n-2)
+    uint64_t bsum1[2];         // sum_{k >= 12} bcoef[k] * bval[k]: the constant part of the step n-2 boundary sum
     uint32_t bcol[22];         // asserted columns
     uint32_t delta;            // LWE delta (fhe/src/parameters.rs:17)
     uint64_t inv_zn[8][2];     // 1 / (x^n - 1) for LDE step i = 8j + c (depends on c only)

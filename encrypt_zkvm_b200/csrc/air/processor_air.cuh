@@ -73,8 +73,13 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
     ar.checkpoint();
     const fe arith = ar.mul(n0b1, n2);                    // !b0 * b1 * !b2
     const fe io = ar.mul(ar.mul(b0, n1), n2);             // b0 * !b1 * !b2
-    const fe f_add = ar.mul(arith, n3n4), f_sadd = ar.mul(arith, b3n4), f_add2 = ar.mul(arith, b3b4);
-    const fe f_mul = ar.mul(arith, n3b4), f_smul = ar.mul(ar.mul(n0b1, b2), n3n4);
+    // A sink that only wants sum_j coef_j * r_j (Sink::kGrouped) gets the constraints that share a selector factor
+    // as coef-weighted sums times that factor: the same field value with fewer products (9 per row), since
+    // multiplication distributes exactly.  add / sadd / mul are then never formed on their own.
+    fe f_add = fe_zero(), f_sadd = fe_zero(), f_mul = fe_zero();
+    if (!Sink::kGrouped) f_add = ar.mul(arith, n3n4), f_sadd = ar.mul(arith, b3n4), f_mul = ar.mul(arith, n3b4);
+    const fe f_add2 = ar.mul(arith, b3b4);
+    const fe f_smul = ar.mul(ar.mul(n0b1, b2), n3n4);
     ar.checkpoint();
     const fe f_push = ar.mul(io, n3n4), f_read = ar.mul(io, n3b4), f_read2 = ar.mul(io, b3n4);
     const fe f_noop = ar.mul(ar.mul(ar.mul(n0, n1), n2), n3n4);
@@ -95,9 +100,15 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
     const fe s0 = f.cur(12), s1 = f.cur(13);
     const fe sn0 = f.nxt(12), sn1 = f.nxt(13);
     // r3: add * (s0' - (s0 + s1))                            constrains.rs:108-110
-    sink.put(ar, 3, ar.mul(f_add, ar.sub(sn0, ar.add(s0, s1))));
     // r6: mul * (s0' - s0*s1)                                constrains.rs:146-148
-    sink.put(ar, 6, ar.mul(f_mul, ar.sub(sn0, ar.mul(s0, s1))));
+    const fe e3 = ar.sub(sn0, ar.add(s0, s1)), e6 = ar.sub(sn0, ar.mul(s0, s1));
+    fe arith_sum = fe_zero();  // grouped: sum over the arith-selected constraints of coef * (b3, b4 selector) * expression
+    if (Sink::kGrouped) {
+        arith_sum = ar.add(ar.mul(n3n4, sink.scaled(ar, 3, e3)), ar.mul(n3b4, sink.scaled(ar, 6, e6)));
+    } else {
+        sink.put(ar, 3, ar.mul(f_add, e3));
+        sink.put(ar, 6, ar.mul(f_mul, e6));
+    }
     ar.checkpoint();
     // ciphertext ops: lwe_size = 5 (SURVEY 8b "constraints discovered")
     {
@@ -115,16 +126,26 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
             acc_smul = ar.add(acc_smul, ar.sub(snj, ar.mul(sj1, s0)));
         }
         ar.checkpoint();
-        sink.put(ar, 4, ar.mul(f_sadd, acc_sadd));
-        sink.put(ar, 5, ar.mul(f_add2, acc_add2));
+        if (Sink::kGrouped) {
+            arith_sum = ar.add(arith_sum, ar.mul(b3n4, sink.scaled(ar, 4, acc_sadd)));
+            arith_sum = ar.add(arith_sum, ar.mul(b3b4, sink.scaled(ar, 5, acc_add2)));
+            sink.add(ar, ar.mul(arith, arith_sum));
+        } else {
+            sink.put(ar, 4, ar.mul(f_sadd, acc_sadd));
+            sink.put(ar, 5, ar.mul(f_add2, acc_add2));
+        }
         sink.put(ar, 7, ar.mul(f_smul, acc_smul));
     }
     ar.checkpoint();
     // r8..r11                                                 constrains.rs:166-180
     {
         const fe d1 = ar.sub(sn1, s0);
-        sink.put(ar, 8, ar.mul(f_push, d1));
-        sink.put(ar, 9, ar.mul(f_read, d1));
+        if (Sink::kGrouped) {
+            sink.add(ar, ar.mul(ar.add(sink.scaled(ar, 8, f_push), sink.scaled(ar, 9, f_read)), d1));
+        } else {
+            sink.put(ar, 8, ar.mul(f_push, d1));
+            sink.put(ar, 9, ar.mul(f_read, d1));
+        }
         sink.put(ar, 10, ar.mul(f_read2, ar.sub(f.nxt(17), s0)));
         sink.put(ar, 11, ar.mul(f_noop, ar.sub(sn0, s0)));
     }
@@ -138,10 +159,16 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
         fe hn[4] = {f.nxt(7), f.nxt(8), f.nxt(9), f.nxt(10)};
         ar.checkpoint();
         // hash copy (r16..r19)
-        sink.put(ar, 16, ar.mul(ar.sub(hn[0], h[0]), gate_copy));
-        sink.put(ar, 17, ar.mul(ar.sub(hn[1], h[1]), gate_copy));
-        sink.put(ar, 18, ar.mul(hn[2], gate_copy));
-        sink.put(ar, 19, ar.mul(hn[3], gate_copy));
+        if (Sink::kGrouped) {
+            fe t = ar.add(sink.scaled(ar, 16, ar.sub(hn[0], h[0])), sink.scaled(ar, 17, ar.sub(hn[1], h[1])));
+            t = ar.add(t, ar.add(sink.scaled(ar, 18, hn[2]), sink.scaled(ar, 19, hn[3])));
+            sink.add(ar, ar.mul(t, gate_copy));
+        } else {
+            sink.put(ar, 16, ar.mul(ar.sub(hn[0], h[0]), gate_copy));
+            sink.put(ar, 17, ar.mul(ar.sub(hn[1], h[1]), gate_copy));
+            sink.put(ar, 18, ar.mul(hn[2], gate_copy));
+            sink.put(ar, 19, ar.mul(hn[3], gate_copy));
+        }
         ar.checkpoint();
         // forward half: MDS * h^3 + ark[0..4], + opcode / pushed value
         fe c[4], step0[4];
@@ -167,8 +194,15 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
         for (int i = 0; i < 4; i++) d[i] = ar.sub(hn[i], periodic[5 + i]);
         rescue_inv_mds(ar, k, d, step1);
         ar.checkpoint();
+        if (Sink::kGrouped) {
+            fe t = fe_zero();
 #pragma unroll
-        for (int i = 0; i < 4; i++) sink.put(ar, 12 + i, ar.mul(ar.sub(ar.cube(step1[i]), step0[i]), gate_round));
+            for (int i = 0; i < 4; i++) t = ar.add(t, sink.scaled(ar, 12 + i, ar.sub(ar.cube(step1[i]), step0[i])));
+            sink.add(ar, ar.mul(t, gate_round));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) sink.put(ar, 12 + i, ar.mul(ar.sub(ar.cube(step1[i]), step0[i]), gate_round));
+        }
     }
 }
 

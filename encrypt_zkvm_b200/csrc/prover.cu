@@ -366,6 +366,11 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
             put(hp.bval[12 + k], k < 2 ? pub.elements[k] : pub.elements[2 + (k - 2)]);
             hp.bcol[12 + k] = cols1[k];
         }
+        {
+            Fp c1;
+            for (uint32_t k = 0; k < 10; k++) c1 = c1 + bc[12 + k] * (k < 2 ? pub.elements[k] : pub.elements[2 + (k - 2)]);
+            put(hp.bsum1, c1);
+        }
         hp.delta = pub.lwe_delta;
         // 1/(x^n - 1): x_i^n = o^n * w_8^(i mod 8)
         const Fp on = pow(o, n), w8 = root_of_unity(3);
