@@ -12,25 +12,31 @@ namespace {
 constexpr int kThreads = 256;
 
 // One thread per row; the table is column-major so a warp reads 32 consecutive 16-byte cells per column.
+// WIDTH > 0: the row width is a compile-time constant (28 trace columns, 7 composition columns, 8 FRI values), so
+// the block loop is unrolled and the block lengths and flags are immediates; WIDTH = 0: any width.
+template <int WIDTH>
 __global__ void __launch_bounds__(kThreads) hash_rows_kernel(const uint4* __restrict__ table, uint64_t pitch,
-                                                            uint32_t width, uint64_t rows, RowShard sh,
+                                                            uint32_t width_rt, uint64_t rows, RowShard sh,
                                                             uint4* __restrict__ leaves) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows) return;
     const uint64_t i = sh.global_row(t);
+    const uint32_t width = WIDTH > 0 ? (uint32_t)WIDTH : width_rt;
     uint32_t cv[8];
     b3_init(cv);
     const uint32_t nblocks = (width + 3) / 4;
-    for (uint32_t b = 0; b < nblocks; b++) {
+    const uint4* cell = table + i;
+#pragma unroll
+    for (uint32_t b = 0; b < (WIDTH > 0 ? (uint32_t)(WIDTH + 3) / 4 : nblocks); b++) {
         uint32_t m[16];
-        uint32_t cells = min(4u, width - 4 * b);
+        const uint32_t cells = min(4u, width - 4 * b);
 #pragma unroll
         for (uint32_t k = 0; k < 4; k++) {
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (k < cells) v = __ldg(table + (uint64_t)(4 * b + k) * pitch + i);
+            if (k < cells) v = __ldg(cell + (uint64_t)(4 * b + k) * pitch);
             m[4 * k] = v.x, m[4 * k + 1] = v.y, m[4 * k + 2] = v.z, m[4 * k + 3] = v.w;
         }
-        uint32_t flags = (b == 0 ? B3_CHUNK_START : 0u) | (b == nblocks - 1 ? (B3_CHUNK_END | B3_ROOT) : 0u);
+        const uint32_t flags = (b == 0 ? B3_CHUNK_START : 0u) | (b == nblocks - 1 ? (B3_CHUNK_END | B3_ROOT) : 0u);
         b3_compress(cv, m, cells * 16, flags);
     }
     leaves[2 * t] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
@@ -102,7 +108,14 @@ int hash_rows_sharded(cudaStream_t s, const uint4* table, uint64_t pitch, uint32
     unsigned blocks = (unsigned)((local_rows + kThreads - 1) / kThreads);
     {
         LaunchScope ls(s, K_HASH_ROWS, local_rows * ((uint64_t)width * 16 + 32));
-        hash_rows_kernel<<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
+        if (width == 28)
+            hash_rows_kernel<28><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
+        else if (width == 7)
+            hash_rows_kernel<7><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
+        else if (width == 8)
+            hash_rows_kernel<8><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
+        else
+            hash_rows_kernel<0><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;
