@@ -186,6 +186,29 @@ def test_prover_state_survives_other_trace_lengths(gpu_prover_factory):
     assert first == second == third
 
 
+def test_two_provers_on_one_gpu_from_two_threads(gpu_prover_factory, oracle):
+    """Proof-level pipelining: provers share nothing, so two host threads may prove at the same time on
+    the same GPU; every proof must still be the oracle's bytes."""
+    import threading
+    ezk = gpu_prover_factory
+    cases = [synthetic(2, 11), synthetic(1, 10)]
+    want = [oracle.prove(c.trace, pub_elements(c.program_hash, c.outputs), _oracle.default_options()).proof for c in cases]
+    got = [[], []]
+
+    def work(k):
+        with ezk.ExecutionProver(ezk.ProofOptions(), cases[k].program_hash, cases[k].outputs, ezk.ServerKey()) as p:
+            for _ in range(6):
+                got[k].append(p.prove(cases[k].trace).to_bytes())
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k in range(2):
+        assert len(got[k]) == 6 and all(g == want[k] for g in got[k])
+
+
 def test_argument_errors(gpu_prover_factory):
     ezk = gpu_prover_factory
     case = synthetic(1, 7)
