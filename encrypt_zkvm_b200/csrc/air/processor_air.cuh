@@ -65,14 +65,19 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
     const fe one = fe_one();
     // op bits: b0 = cur[5] (MSB) ... b4 = cur[1] (LSB)   (flags.rs:15-35)
     const fe b0 = f.cur(5), b1 = f.cur(4), b2 = f.cur(3), b3 = f.cur(2), b4 = f.cur(1);
-    const fe n0 = ar.sub(one, b0), n1 = ar.sub(one, b1), n2 = ar.sub(one, b2), n3 = ar.sub(one, b3), n4 = ar.sub(one, b4);
-    // shared sub-products of the degree-5 selectors (flags.rs:45-79); same field values as the reference's
-    // left-to-right products because multiplication in the field is exact
-    const fe n3n4 = ar.mul(n3, n4), b3n4 = ar.mul(b3, n4), b3b4 = ar.mul(b3, b4), n3b4 = ar.mul(n3, b4);
-    const fe n0b1 = ar.mul(n0, b1);
+    const fe n2 = ar.sub(one, b2);
+    // Products of complemented bits expand into one product and a few differences, e.g. (1 - b3)(1 - b4) =
+    // 1 - b3 - b4 + b3 b4: the same field elements as the reference's left-to-right products (flags.rs:45-79),
+    // because the field operations are exact, with 6 products fewer per row.
+    const fe b3b4 = ar.mul(b3, b4);
+    const fe b3n4 = ar.sub(b3, b3b4), n3b4 = ar.sub(b4, b3b4);
+    const fe n3n4 = ar.sub(ar.sub(one, b3), n3b4);            // 1 - b3 - (b4 - b3 b4)
+    const fe b0b1 = ar.mul(b0, b1);                            // also constraint r2
+    const fe n0b1 = ar.sub(b1, b0b1), b0n1 = ar.sub(b0, b0b1);
+    const fe n0n1 = ar.sub(ar.sub(one, b0), n0b1);            // 1 - b0 - (b1 - b0 b1)
     ar.checkpoint();
     const fe arith = ar.mul(n0b1, n2);                    // !b0 * b1 * !b2
-    const fe io = ar.mul(ar.mul(b0, n1), n2);             // b0 * !b1 * !b2
+    const fe io = ar.mul(b0n1, n2);                       // b0 * !b1 * !b2
     // A sink that only wants sum_j coef_j * r_j (Sink::kGrouped) gets the constraints that share a selector factor
     // as coef-weighted sums times that factor: the same field value with fewer products (9 per row), since
     // multiplication distributes exactly.  add / sadd / mul are then never formed on their own.
@@ -82,7 +87,7 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
     const fe f_smul = ar.mul(ar.mul(n0b1, b2), n3n4);
     ar.checkpoint();
     const fe f_push = ar.mul(io, n3n4), f_read = ar.mul(io, n3b4), f_read2 = ar.mul(io, b3n4);
-    const fe f_noop = ar.mul(ar.mul(ar.mul(n0, n1), n2), n3n4);
+    const fe f_noop = ar.mul(ar.mul(n0n1, n2), n3n4);
 
     ar.checkpoint();
     // r0: clk' - (clk + 1)                                   constrains.rs:95-97
@@ -91,11 +96,10 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
     {
         fe t = ar.sub(ar.sub(f.nxt(11), f.cur(11)), b0);
         t = ar.add(t, b1);
-        t = ar.sub(t, ar.mul_small(f_read2, 4));
-        sink.put(ar, 1, ar.add(t, ar.mul_small(f_add2, 4)));
+        sink.put(ar, 1, ar.add(t, ar.mul_small(ar.sub(f_add2, f_read2), 4)));  // - 4 read2 + 4 add2
     }
     // r2: shr * shl                                          constrains.rs:99-101
-    sink.put(ar, 2, ar.mul(b0, b1));
+    sink.put(ar, 2, b0b1);
 
     const fe s0 = f.cur(12), s1 = f.cur(13);
     const fe sn0 = f.nxt(12), sn1 = f.nxt(13);
@@ -112,19 +116,24 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
     ar.checkpoint();
     // ciphertext ops: lwe_size = 5 (SURVEY 8b "constraints discovered")
     {
-        fe acc_sadd = fe_zero(), acc_add2 = fe_zero(), acc_smul = fe_zero();
+        // The three sums run over the same next-row cells: with N = sum_j s'_j and C1 = sum_j s_{1+j},
+        //   sadd: sum_j (s'_j - ct_j) with ct = s_{1..5} + trivial(delta * s0)   = N - C1 - delta s0
+        //         (constrains.rs:112-126, server_key.rs:78-83,104-114)
+        //   add2: sum_j (s'_j - (s_j + s_{5+j}))                                 = N - sum_{j<10} s_j
+        //         (constrains.rs:128-144, server_key.rs:89-102)
+        //   smul: sum_j (s'_j - s0 s_{1+j})                                      = N - s0 C1   (ONE product)
+        //         (constrains.rs:150-164, server_key.rs:116-124)
+        fe nsum = fe_zero(), c1 = fe_zero(), lo10 = fe_zero();
 #pragma unroll
         for (int j = 0; j < 5; j++) {
-            const fe snj = f.nxt(12 + j), sj = f.cur(12 + j), sj1 = f.cur(13 + j), sj5 = f.cur(17 + j);
-            // sadd: out = ct + trivial(delta * s0)             constrains.rs:112-126, server_key.rs:78-83,104-114
-            fe out = sj1;
-            if (j == 4) out = ar.add(out, ar.mul_small(s0, delta));
-            acc_sadd = ar.add(acc_sadd, ar.sub(snj, out));
-            // add2: s_j + s_{5+j}                              constrains.rs:128-144, server_key.rs:89-102
-            acc_add2 = ar.add(acc_add2, ar.sub(snj, ar.add(sj, sj5)));
-            // smul: s0 * s_{1+j}                               constrains.rs:150-164, server_key.rs:116-124
-            acc_smul = ar.add(acc_smul, ar.sub(snj, ar.mul(sj1, s0)));
+            nsum = ar.add(nsum, f.nxt(12 + j));
+            c1 = ar.add(c1, f.cur(13 + j));
         }
+#pragma unroll
+        for (int j = 0; j < 10; j++) lo10 = ar.add(lo10, f.cur(12 + j));
+        const fe acc_sadd = ar.sub(ar.sub(nsum, c1), ar.mul_small(s0, delta));
+        const fe acc_add2 = ar.sub(nsum, lo10);
+        const fe acc_smul = ar.sub(nsum, ar.mul(s0, c1));
         ar.checkpoint();
         if (Sink::kGrouped) {
             arith_sum = ar.add(arith_sum, ar.mul(b3n4, sink.scaled(ar, 4, acc_sadd)));
@@ -179,12 +188,11 @@ __device__ __forceinline__ void eval_transition(A& ar, const Frame& f, const fe*
         ar.checkpoint();
 #pragma unroll
         for (int i = 0; i < 4; i++) step0[i] = ar.add(step0[i], periodic[1 + i]);
-        // opcode = 16 b0 + 8 b1 + 4 b2 + 2 b3 + b4              flags.rs:81-87
-        fe opcode = ar.mul_small(b0, 16);
-        opcode = ar.add(opcode, ar.mul_small(b1, 8));
-        opcode = ar.add(opcode, ar.mul_small(b2, 4));
-        opcode = ar.add(opcode, ar.mul_small(b3, 2));
-        opcode = ar.add(opcode, b4);
+        // opcode = 16 b0 + 8 b1 + 4 b2 + 2 b3 + b4 (flags.rs:81-87), by doubling
+        fe opcode = ar.add(ar.add(b0, b0), b1);
+        opcode = ar.add(ar.add(opcode, opcode), b2);
+        opcode = ar.add(ar.add(opcode, opcode), b3);
+        opcode = ar.add(ar.add(opcode, opcode), b4);
         step0[0] = ar.add(step0[0], opcode);
         step0[1] = ar.add(step0[1], ar.mul(sn0, f_push));
         ar.checkpoint();
