@@ -31,40 +31,54 @@ inline Fp operator+(Fp a, Fp b) {
 inline Fp operator-(Fp a, Fp b) { return Fp(a.v >= b.v ? a.v - b.v : a.v + (Fp::modulus() - b.v)); }
 inline Fp operator-(Fp a) { return Fp(a.v ? Fp::modulus() - a.v : 0); }
 
-// x * 2^128 = x * (45*2^40 - 1) (mod M): shift-and-subtract form, applied to a 128-bit `hi`
-// word of a 256-bit product; the partial result is folded again until it fits in 128 bits.
+// Multiplication: schoolbook 2x2 product of 64-bit limbs, then two folds with 2^128 = 45*2^40 - 1 (mod M).
+//   value = L + H*2^128 = L + (H*45 << 40) - H          (H*45 << 40 >= H, so the difference never borrows out)
+// After the first fold the part above 2^128 is < 2^47, after the second it is 0 or 1.  Branches are on
+// events of probability ~2^-35 (carry of the second fold) and on the final canonical subtraction only, so
+// independent products interleave in the out-of-order core (the VM's Rescue sponge runs four at a time).
+namespace detail {
+inline Fp fold256(uint64_t r0, uint64_t r1, uint64_t r2, uint64_t r3) {
+    const u128 m0 = (u128)r2 * 45, m1 = (u128)r3 * 45 + (uint64_t)(m0 >> 64);
+    const uint64_t h0 = (uint64_t)m0, h1 = (uint64_t)m1, h2 = (uint64_t)(m1 >> 64);
+    const uint64_t s0 = h0 << 40, s1 = (h1 << 40) | (h0 >> 24), s2 = (h2 << 40) | (h1 >> 24);
+    u128 acc = (u128)r0 + s0;
+    const uint64_t t0 = (uint64_t)acc;
+    acc = (acc >> 64) + r1 + s1;
+    const uint64_t t1 = (uint64_t)acc;
+    uint64_t t2 = s2 + (uint64_t)(acc >> 64);
+    const u128 x = ((u128)t1 << 64) | t0, h = ((u128)r3 << 64) | r2;
+    const u128 y = x - h;
+    t2 -= (x < h);                                       // < 2^47
+    const u128 add = (((u128)t2 * 45) << 40) - t2;       // t2 * (45*2^40 - 1) < 2^93
+    u128 z = y + add;
+    if (z < y) z += (((u128)45) << 40) - 1;              // wrapped past 2^128: z is small, one more fold
+    return Fp::reduce(z);
+}
+}  // namespace detail
+
 inline Fp operator*(Fp a, Fp b) {
     const uint64_t a0 = (uint64_t)a.v, a1 = (uint64_t)(a.v >> 64), b0 = (uint64_t)b.v, b1 = (uint64_t)(b.v >> 64);
-    const u128 ll = (u128)a0 * b0, lh = (u128)a0 * b1, hl = (u128)a1 * b0, hh = (u128)a1 * b1;
-    u128 cross = lh + hl;
-    const u128 cross_carry = cross < lh ? ((u128)1 << 64) : 0;
-    u128 lo = ll + (cross << 64);
-    u128 hi = hh + (cross >> 64) + cross_carry + (lo < ll ? 1 : 0);
-    // fold while hi != 0: value = lo + hi*2^128 = lo + (hi*45 << 40) - hi
-    while (hi != 0) {
-        // hi*45 as 192 bits
-        const u128 h_lo = (u128)(uint64_t)hi * 45, h_hi = (u128)(uint64_t)(hi >> 64) * 45;
-        const u128 m_lo = h_lo + (h_hi << 64);
-        const u128 m_hi = (h_hi >> 64) + (m_lo < h_lo ? 1 : 0);
-        // (m << 40) as up to 256 bits: s_hi:s_lo
-        const u128 s_lo = m_lo << 40;
-        const u128 s_hi = (m_hi << 40) | (m_lo >> 88);
-        // lo + s - hi
-        u128 nlo = lo + s_lo;
-        u128 nhi = s_hi + (nlo < lo ? 1 : 0);
-        if (nlo < hi) nhi -= 1;  // borrow (total is non-negative because s >= hi)
-        nlo -= hi;
-        lo = nlo;
-        hi = nhi;
-    }
-    return Fp::reduce(lo);
+    const u128 p00 = (u128)a0 * b0, p01 = (u128)a0 * b1, p10 = (u128)a1 * b0, p11 = (u128)a1 * b1;
+    u128 t = (p00 >> 64) + (uint64_t)p01 + (uint64_t)p10;
+    const uint64_t r1 = (uint64_t)t;
+    t = (t >> 64) + (p01 >> 64) + (p10 >> 64) + (uint64_t)p11;
+    return detail::fold256((uint64_t)p00, r1, (uint64_t)t, (uint64_t)(p11 >> 64) + (uint64_t)(t >> 64));
+}
+
+inline Fp square(Fp a) {
+    const uint64_t a0 = (uint64_t)a.v, a1 = (uint64_t)(a.v >> 64);
+    const u128 p00 = (u128)a0 * a0, p01 = (u128)a0 * a1, p11 = (u128)a1 * a1;
+    u128 t = (p00 >> 64) + 2 * (u128)(uint64_t)p01;
+    const uint64_t r1 = (uint64_t)t;
+    t = (t >> 64) + 2 * (p01 >> 64) + (uint64_t)p11;
+    return detail::fold256((uint64_t)p00, r1, (uint64_t)t, (uint64_t)(p11 >> 64) + (uint64_t)(t >> 64));
 }
 
 inline Fp pow(Fp b, u128 e) {
     Fp r(1);
     while (e) {
         if (e & 1) r = r * b;
-        b = b * b;
+        b = square(b);
         e >>= 1;
     }
     return r;

@@ -36,10 +36,103 @@ const char* op_name(uint8_t code) {
     return "?";
 }
 
+// Inverse S-box x -> x^INV_ALPHA on the four state elements at once (crypto/src/rescue.rs:146-150 with
+// INV_ALPHA :199).  The exponent is (2(M-1)+1)/3 = 0xAAAAAAAAAAAAAAAAAAAA8CAAAAAAAAAB: runs of the bit pair
+// "10" around one irregular byte.  With A_k = x^("10" repeated k times), A_(j+k) = A_j^(4^k) * A_k, the chain
+// below needs 127 squarings + 14 products instead of 127 + 63 for square-and-multiply, and every step is
+// applied to the four independent lanes back to back so that their multiplications overlap in the core.
+// The trace builder spends its time here: one call per executed operation, each depending on the last.
+//
+// fmul: the field product of f128_host.h (same folds, same result) as one x86-64 block: 6 `mulq` and ~40
+// single-cycle instructions, where the compiler's code for the portable form is ~110 (measured: 8.9 ns against
+// 15.7 ns per product with four lanes in flight).  Other hosts use the portable operator.
+#if defined(__x86_64__) && defined(__GNUC__)
+inline Fp fmul(Fp a, Fp b) {
+    typedef unsigned long long ull;
+    const ull a0 = (ull)a.v, a1 = (ull)(a.v >> 64), b0 = (ull)b.v, b1 = (ull)(b.v >> 64);
+    ull w0, w1, w2, w3, t, u;
+    unsigned char cf;
+    __asm__(
+        // 256-bit product w3:w2:w1:w0
+        "movq %[a0], %%rax\n\t mulq %[b0]\n\t movq %%rax, %[w0]\n\t movq %%rdx, %[w1]\n\t"
+        "movq %[a1], %%rax\n\t mulq %[b1]\n\t movq %%rax, %[w2]\n\t movq %%rdx, %[w3]\n\t"
+        "movq %[a0], %%rax\n\t mulq %[b1]\n\t addq %%rax, %[w1]\n\t adcq %%rdx, %[w2]\n\t adcq $0, %[w3]\n\t"
+        "movq %[a1], %%rax\n\t mulq %[b0]\n\t addq %%rax, %[w1]\n\t adcq %%rdx, %[w2]\n\t adcq $0, %[w3]\n\t"
+        // H*45 = rdx:rax:u, shifted left by 40
+        "movq %[w2], %%rax\n\t mulq %[k]\n\t movq %%rax, %[u]\n\t movq %%rdx, %[t]\n\t"
+        "movq %[w3], %%rax\n\t mulq %[k]\n\t addq %[t], %%rax\n\t adcq $0, %%rdx\n\t"
+        "shldq $40, %%rax, %%rdx\n\t"
+        "shldq $40, %[u], %%rax\n\t"
+        "shlq $40, %[u]\n\t"
+        // L + (H*45 << 40) - H  ->  rdx:w1:w0, rdx < 2^47
+        "addq %[u], %[w0]\n\t adcq %%rax, %[w1]\n\t adcq $0, %%rdx\n\t"
+        "subq %[w2], %[w0]\n\t sbbq %[w3], %[w1]\n\t sbbq $0, %%rdx\n\t"
+        // second fold: + rdx*(45*2^40 - 1)
+        "leaq (%%rdx,%%rdx,4), %%rax\n\t leaq (%%rax,%%rax,8), %%rax\n\t"
+        "movq %%rax, %[t]\n\t shlq $40, %%rax\n\t shrq $24, %[t]\n\t subq %%rdx, %%rax\n\t sbbq $0, %[t]\n\t"
+        "addq %%rax, %[w0]\n\t adcq %[t], %[w1]\n\t setc %[cf]"
+        : [w0] "=&r"(w0), [w1] "=&r"(w1), [w2] "=&r"(w2), [w3] "=&r"(w3), [t] "=&r"(t), [u] "=&r"(u), [cf] "=q"(cf)
+        : [a0] "r"(a0), [a1] "r"(a1), [b0] "r"(b0), [b1] "r"(b1), [k] "r"(45ULL)
+        : "rax", "rdx", "cc");
+    u128 z = ((u128)w1 << 64) | w0;
+    if (__builtin_expect(cf, 0)) z += (((u128)45) << 40) - 1;
+    return Fp::reduce(z);
+}
+#else
+inline Fp fmul(Fp a, Fp b) { return a * b; }
+#endif
+
+struct Lanes {
+    Fp v[4];
+};
+inline Lanes sqr_n(Lanes a, int n) {
+    for (int k = 0; k < n; k++)
+        for (int i = 0; i < 4; i++) a.v[i] = fmul(a.v[i], a.v[i]);
+    return a;
+}
+inline Lanes mul(Lanes a, const Lanes& b) {
+    for (int i = 0; i < 4; i++) a.v[i] = fmul(a.v[i], b.v[i]);
+    return a;
+}
+void inv_sbox(Fp s[4]) {
+    Lanes x;
+    for (int i = 0; i < 4; i++) x.v[i] = s[i];
+    const Lanes a1 = sqr_n(x, 1);
+    const Lanes a2 = mul(sqr_n(a1, 2), a1);
+    const Lanes a4 = mul(sqr_n(a2, 4), a2);
+    const Lanes a8 = mul(sqr_n(a4, 8), a4);
+    const Lanes a16 = mul(sqr_n(a8, 16), a8);
+    const Lanes a18 = mul(sqr_n(a16, 4), a2);
+    const Lanes a36 = mul(sqr_n(a18, 36), a18);
+    Lanes r = mul(sqr_n(a36, 8), a4);  // bits 127..48: "10" x 40
+    r = mul(sqr_n(r, 1), x);           // 0x8C = 1000 1100
+    r = mul(sqr_n(r, 4), x);
+    r = mul(sqr_n(r, 1), x);
+    r = sqr_n(r, 2);
+    r = mul(sqr_n(r, 36), a18);        // bits 39..4: "10" x 18
+    r = mul(sqr_n(r, 1), x);           // 0xB = 1011
+    r = mul(sqr_n(r, 2), x);
+    r = mul(sqr_n(r, 1), x);
+    for (int i = 0; i < 4; i++) s[i] = r.v[i];
+}
+
+// The chain's exponent is written out by hand above; tie it to the constant of the reference once per process.
+bool inv_sbox_matches_inv_alpha() {
+    Fp probe[4] = {Fp(2), Fp(Fp::modulus() - 1), Fp((((u128)0x0123456789ABCDEFULL) << 64) | 0xFEDCBA9876543210ULL), Fp(0)};
+    Fp want[4];
+    for (int i = 0; i < 4; i++) want[i] = pow(probe[i], kInvAlpha);
+    inv_sbox(probe);
+    for (int i = 0; i < 4; i++)
+        if (probe[i] != want[i] || fmul(fmul(probe[i], probe[i]), probe[i]) != pow(want[i], 3) ||
+            fmul(want[i], want[(i + 1) & 3]) != want[i] * want[(i + 1) & 3])
+            return false;
+    return true;
+}
+
 void mds_mul(Fp s[4]) {  // crypto/src/rescue.rs:162-176
     Fp r[4];
     for (int i = 0; i < 4; i++)
-        for (int j = 0; j < 4; j++) r[i] = r[i] + cst(kMds[i * 4 + j]) * s[j];
+        for (int j = 0; j < 4; j++) r[i] = r[i] + fmul(cst(kMds[i * 4 + j]), s[j]);
     for (int i = 0; i < 4; i++) s[i] = r[i];
 }
 
@@ -120,14 +213,16 @@ std::string Operation::to_string() const {
 }
 
 void RescueSponge::update(uint8_t op_code, uint8_t op_value) {
+    static const bool chain_ok = inv_sbox_matches_inv_alpha();
+    if (!chain_ok) throw VmError{"internal error: inverse S-box chain does not compute x^INV_ALPHA"};
     if (step % kCycle < kRounds) {  // rescue.rs:42-54, 102-118
         const Pair64* ark = &kArk[(step % kCycle) * 8];
-        for (int i = 0; i < 4; i++) state[i] = state[i] * state[i] * state[i];
+        for (int i = 0; i < 4; i++) state[i] = fmul(fmul(state[i], state[i]), state[i]);
         mds_mul(state);
         for (int i = 0; i < 4; i++) state[i] = state[i] + cst(ark[i]);
         state[0] = state[0] + Fp::from_u64(op_code);
         state[1] = state[1] + Fp::from_u64(op_value);
-        for (int i = 0; i < 4; i++) state[i] = pow(state[i], kInvAlpha);
+        inv_sbox(state);
         mds_mul(state);
         for (int i = 0; i < 4; i++) state[i] = state[i] + cst(ark[4 + i]);
     } else {
@@ -163,7 +258,11 @@ Program Program::compile(const std::string& source) {
     }
     p.code.resize(pad_to_cycle(p.code.size()), noop);  // mod.rs:85-86 (pads a full cycle when already aligned)
     RescueSponge sponge;
-    for (const auto& op : p.code) sponge.update(op.code, op.value);
+    p.sponge_states.resize(4 * p.code.size());
+    for (size_t i = 0; i < p.code.size(); i++) {
+        sponge.update(p.code[i].code, p.code[i].value);
+        for (int j = 0; j < 4; j++) p.sponge_states[4 * i + j] = sponge.state[j];
+    }
     p.hash[0] = sponge.state[0];
     p.hash[1] = sponge.state[1];
     return p;
@@ -190,6 +289,7 @@ ExecutionTrace execute(const Program& program, const std::vector<uint8_t>& pub, 
     RescueSponge sponge;
     size_t depth = 0, tape_a = 0, tape_b = 0, clk = 0;
     const size_t num_ct = lw ? secret.size() / lw : 0;
+    const bool have_states = program.sponge_states.size() == 4 * num_ops;
 
     auto stack_err = [&](const Operation& op, const std::string& what) {
         throw VmError{"stack error at " + std::to_string(clk) + ": " + what};
@@ -264,7 +364,12 @@ ExecutionTrace execute(const Program& program, const std::vector<uint8_t>& pub, 
         for (int i = 0; i < 5; i++) bits[i][clk - 1] = Fp::from_u64((op.code >> i) & 1);  // decoder.rs:68-76
         if (sponge.step % kCycle >= kRounds && op.code != OP_NOOP)                   // chiplets.rs:92-95
             throw VmError{"chiplets error at " + std::to_string(clk) + ": expected noop but was " + op.to_string()};
-        sponge.update(op.code, op.value);
+        if (have_states) {  // the chain compile() already ran over the same operations
+            for (int i = 0; i < 4; i++) sponge.state[i] = program.sponge_states[4 * (clk - 1) + i];
+            sponge.step++;
+        } else {
+            sponge.update(op.code, op.value);
+        }
         flag_col[clk - 1] = Fp(1);                                                   // chiplets.rs:99-105
         for (int i = 0; i < 4; i++) sponge_cols[i][clk] = sponge.state[i];           // chiplets.rs:107-109
     }

@@ -45,6 +45,11 @@ struct RescueSponge {  // crypto/src/rescue.rs:16-60
 struct Program {
     std::vector<Operation> code;
     Fp hash[2];
+    // Sponge state after each operation (4 elements per op), kept from the hashing pass of compile():
+    // the chiplet columns of the trace are this same chain (chiplets.rs:92-112), and it is the one
+    // inherently sequential, expensive part of the VM (one 128-bit exponentiation per lane per op), so
+    // execute() copies it instead of running the chain a second time.  Empty => execute() recomputes.
+    std::vector<Fp> sponge_states;
     // throws VmError("program error at {step}: {message}")
     static Program compile(const std::string& source);
     std::string to_string() const;  // "push(1) noop ..." (program/mod.rs:128-138)

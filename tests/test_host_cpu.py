@@ -115,6 +115,26 @@ def test_program_hash_is_the_rescue_sponge_over_the_padded_code():
     assert prog.hash() == sponge_hash(prog.code())
 
 
+def test_sponge_chain_over_long_programs_and_the_trace_columns_it_feeds():
+    """The VM computes x^INV_ALPHA (crypto/src/rescue.rs:146-150,199) with a fixed addition chain on four lanes
+    and keeps the per-operation states of Program::compile's hashing pass for the chiplet columns
+    (vm/src/processor/chiplets.rs:92-112).  Both must equal the plain big-int sponge, step by step."""
+    from tests._frames import apply_round
+    for kind in (1, 2, 3):
+        prog, ex = ezk.synthetic_case(kind, 12)
+        code = prog.code()
+        assert len(code) >= 1024 and prog.hash() == sponge_hash(code)
+        t = ex.trace()
+        state = [0, 0, 0, 0]
+        for step, (op, value) in enumerate(code):
+            assert _row(t, step)[7:11] == state
+            if step % 16 < 14:
+                state = apply_round(state, op, value, step)
+            else:
+                state[2] = state[3] = 0
+        assert _row(t, len(code))[7:11] == state and state[:2] == prog.hash()
+
+
 # ------------------------------------------------------------------------------------------------ processor
 def _run(source, public=(), secret=()):
     prog = ezk.Program.compile(source)
