@@ -550,7 +550,8 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
 
     // ---- (7) openings + serialization ----
     ProofWriter w;
-    w.u8((uint8_t)kWidth), w.u8(0), w.u8((uint8_t)log_n), w.u16(0);  // TraceInfo
+    // TraceInfo: main width, aux width, aux random elements, log2(length), metadata length
+    w.u8((uint8_t)kWidth), w.u8(0), w.u8(0), w.u8((uint8_t)log_n), w.u16(0);
     w.u8(16);
     w.element(Fp(Fp::modulus()));
     w.u8((uint8_t)opt.num_queries), w.u8((uint8_t)opt.blowup), w.u8((uint8_t)opt.grinding), w.u8((uint8_t)opt.field_ext);

@@ -102,10 +102,11 @@ void GpuProver::verify(const uint8_t* proof, size_t proof_len, const PublicInput
     try {
         Reader r{proof, proof_len};
         // ---- Proof::context ----
-        const uint32_t W = (uint32_t)r.le(1), aux = (uint32_t)r.le(1), log_n = (uint32_t)r.le(1), meta = (uint32_t)r.le(2);
+        const uint32_t W = (uint32_t)r.le(1), aux = (uint32_t)r.le(1), aux_rands = (uint32_t)r.le(1);
+        const uint32_t log_n = (uint32_t)r.le(1), meta = (uint32_t)r.le(2);
         const uint32_t modlen = (uint32_t)r.le(1);
         const uint8_t* modb = r.bytes(16);
-        if (!r.ok || W != kWidth || aux != 0 || meta != 0 || modlen != 16 || log_n < 6 || log_n > 32 ||
+        if (!r.ok || W != kWidth || aux != 0 || aux_rands != 0 || meta != 0 || modlen != 16 || log_n < 6 || log_n > 32 ||
             fp_load(modb).v != Fp::modulus())
             throw Reject{"malformed proof context"};
         ProofOptions opt;
@@ -115,8 +116,11 @@ void GpuProver::verify(const uint8_t* proof, size_t proof_len, const PublicInput
             throw Reject{"unsupported proof options"};
         const uint64_t n = 1ull << log_n, L = 8 * n;
         const uint32_t log_L = log_n + 3;
-        {   // conjectured security: min(queries * log2(blowup) + grinding, 128, 128 - log2 L) - 1
-            const uint32_t sec = std::min(std::min(opt.num_queries * 3 + opt.grinding, 128u), 128u - log_L) - 1;
+        {   // conjectured security: min(min(128 - log2 L, queries * log2(blowup) [+ grinding]) - 1, 128); grinding
+            // bits count only once the queries alone reach 80 bits (winter-air's GRINDING_CONTRIBUTION_FLOOR)
+            uint32_t query_bits = opt.num_queries * 3;
+            if (query_bits >= 80) query_bits += opt.grinding;
+            const uint32_t sec = std::min(std::min(query_bits, 128u - log_L) - 1, 128u);
             if (sec < min_security) throw Reject{"proof does not reach the required conjectured security level"};
         }
         const uint32_t num_unique = (uint32_t)r.le(1);

@@ -151,7 +151,7 @@ long orc_validate_trace(const u128* const* cols, size_t n, const u128* pub18, ui
 struct OrcOptions {
     uint32_t num_queries, blowup, grinding, field_ext, fri_fold, fri_rem_max_deg;
     uint32_t lwe_k, delta;
-    uint32_t compat_ood_interleaved, compat_remainder_low_to_high;
+    uint32_t compat_ood_interleaved, compat_remainder_low_to_high, compat_trace_info_aux_rands_byte;
     uint64_t compat_first_nonce;
 };
 
@@ -161,6 +161,7 @@ static void split(const OrcOptions* o, ProofOptions& po, AirParams& ap, Compat& 
     ap.lwe_k = o->lwe_k, ap.delta = o->delta;
     cp.ood_interleaved = o->compat_ood_interleaved != 0;
     cp.remainder_low_to_high = o->compat_remainder_low_to_high != 0;
+    cp.trace_info_aux_rands_byte = o->compat_trace_info_aux_rands_byte != 0;
     cp.first_nonce = o->compat_first_nonce;
 }
 

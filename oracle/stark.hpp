@@ -31,6 +31,10 @@ struct Compat {
     bool ood_interleaved = true;       // A.7: [cur_0, next_0, cur_1, next_1, ...]
     bool remainder_low_to_high = true; // A.9
     uint64_t first_nonce = 1;          // A.3 (7): grind search starts at 1
+    // A.10: TraceInfo::write_into stores main width, aux width AND the aux segment's random-element count
+    // (all u8) before log2(length): TraceInfo::read_from rebuilds itself through new_multi_segment(main, aux,
+    // num_aux_rands, length, meta), so the count has to be on the wire.  false = the two-byte form.
+    bool trace_info_aux_rands_byte = true;
 };
 
 struct ProofOptions {  // vm/src/lib.rs:20
@@ -612,7 +616,9 @@ static inline void prove(const u128* const* cols, size_t n, const u128* pub18, c
     // (8) assemble the proof (App. A.10)
     ByteWriter w;
     // Context: TraceInfo, modulus bytes, options
-    w.u8((uint8_t)W), w.u8(0), w.u8((uint8_t)lgn), w.u16(0);
+    w.u8((uint8_t)W), w.u8(0);                     // TraceInfo: main width, aux width
+    if (cp.trace_info_aux_rands_byte) w.u8(0);     //            aux random elements
+    w.u8((uint8_t)lgn), w.u16(0);                  //            log2(length), metadata length
     w.u8(16);
     w.elem(MOD);
     w.u8((uint8_t)opt.num_queries), w.u8((uint8_t)opt.blowup), w.u8((uint8_t)opt.grinding), w.u8((uint8_t)opt.field_ext);
@@ -741,9 +747,10 @@ static inline int verify(const uint8_t* proof, size_t proof_len, const u128* pub
                          unsigned min_conjectured_security, const Compat& cp) {
     ByteReader r(proof, proof_len);
     // Context
-    unsigned W = r.u8(), aux = r.u8(), lgn = r.u8(), meta = r.u16();
+    unsigned W = r.u8(), aux = r.u8(), aux_rands = cp.trace_info_aux_rands_byte ? r.u8() : 0;
+    unsigned lgn = r.u8(), meta = r.u16();
     unsigned modlen = r.u8();
-    if (!r.ok || W != TRACE_WIDTH || aux != 0 || meta != 0 || modlen != 16 || lgn < 4 || lgn > 32) return VERIFY_MALFORMED;
+    if (!r.ok || W != TRACE_WIDTH || aux != 0 || aux_rands != 0 || meta != 0 || modlen != 16 || lgn < 4 || lgn > 32) return VERIFY_MALFORMED;
     const uint8_t* modb = r.bytes(16);
     if (!modb || load_le(modb) != MOD) return VERIFY_MALFORMED;
     ProofOptions opt;
@@ -751,9 +758,11 @@ static inline int verify(const uint8_t* proof, size_t proof_len, const u128* pub
     opt.fri_fold = r.u8(), opt.fri_rem_max_deg = r.u8();
     if (!r.ok || opt.field_ext != 1 || opt.fri_fold != 8 || opt.blowup != 8 || opt.num_queries == 0) return VERIFY_OPTIONS;
     const size_t n = (size_t)1 << lgn, B = opt.blowup, L = n * B, C = NUM_COMP_COLUMNS, F = opt.fri_fold;
-    {   // conjectured security (App. A.2): min(queries*log2(blowup) + grinding, 128, 128 - log2 L) - 1
-        unsigned a = opt.num_queries * ilog2(B) + opt.grinding, b = 128, c = 128 - ilog2(L);
-        unsigned sec = std::min(a, std::min(b, c)) - 1;
+    {   // conjectured security (App. A.2): min(min(128 - log2 L, queries*log2(blowup) [+ grinding]) - 1, 128);
+        // the grinding bits only count once the queries alone give 80 bits (GRINDING_CONTRIBUTION_FLOOR)
+        unsigned a = opt.num_queries * ilog2(B), b = 128, c = 128 - ilog2(L);
+        if (a >= 80) a += opt.grinding;
+        unsigned sec = std::min(std::min(a, c) - 1, b);
         if (sec < min_conjectured_security) return VERIFY_SECURITY;
     }
     unsigned num_unique = r.u8();

@@ -19,12 +19,13 @@ ART = {name: i for i, name in enumerate([
 
 class OrcOptions(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("num_queries", "blowup", "grinding", "field_ext", "fri_fold", "fri_rem_max_deg",
-                                          "lwe_k", "delta", "compat_ood_interleaved", "compat_remainder_low_to_high")]
+                                          "lwe_k", "delta", "compat_ood_interleaved", "compat_remainder_low_to_high",
+                                          "compat_trace_info_aux_rands_byte")]
     _fields_.append(("compat_first_nonce", C.c_uint64))
 
 
 def default_options(delta=16, lwe_k=4, **kw) -> OrcOptions:
-    o = OrcOptions(32, 8, 0, 1, 8, 127, lwe_k, delta, 1, 1, 1)
+    o = OrcOptions(32, 8, 0, 1, 8, 127, lwe_k, delta, 1, 1, 1, 1)
     for k, v in kw.items():
         setattr(o, k, v)
     return o

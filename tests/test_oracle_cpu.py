@@ -227,6 +227,27 @@ def test_verifier_rejects_mutations_and_wrong_public_inputs(oracle):
     assert oracle.verify(proof, pub, min_security=128) != 0  # 32 queries * 3 bits - 1 = 95 < 128
 
 
+def test_proof_context_bytes_and_conjectured_security(oracle):
+    """winter-air 0.9.0 `Context::write_into`: TraceInfo = u8 main width, u8 aux width, u8 aux random elements,
+    u8 log2(length), u16 metadata length; then u8 16 + the modulus bytes; then the six option bytes and the number of
+    unique queries.  `get_conjectured_security`: min(min(128 - log2 L, queries*log2(blowup) [+ grinding]) - 1, 128),
+    the grinding bits counting only from 80 query bits on (GRINDING_CONTRIBUTION_FLOOR)."""
+    case = small_case()
+    pub = case.program_hash + case.outputs
+    proof = oracle.prove(case.trace, pub).proof
+    assert proof[:6] == bytes([28, 0, 0, 7, 0, 0])
+    assert proof[6] == 16 and int.from_bytes(proof[7:23], "little") == M
+    assert proof[23:29] == bytes([32, 8, 0, 1, 8, 127]) and proof[29] <= 32
+    two_byte = oracle.prove(case.trace, pub, _oracle.default_options(compat_trace_info_aux_rands_byte=0)).proof
+    assert two_byte == proof[:2] + proof[3:]  # the switch moves nothing else (the context bytes are not hashed)
+    assert oracle.verify(two_byte, pub) != 0
+    for queries, grinding, bits in ((27, 4, 84), (20, 8, 59), (26, 8, 77)):
+        opt = _oracle.default_options(num_queries=queries, grinding=grinding)
+        p = oracle.prove(case.trace, pub, opt).proof
+        assert oracle.verify(p, pub, opt, min_security=bits) == 0
+        assert oracle.verify(p, pub, opt, min_security=bits + 1) != 0
+
+
 def test_prover_rejects_invalid_trace(oracle):
     case = synthetic(1, 7)
     pub = case.program_hash + case.outputs
