@@ -1,6 +1,8 @@
 // GPU prover orchestration: one stream, device workspace, host transcript.  See prover.h.
 // Stage order follows winter-prover 0.9.0 `Prover::prove`.
 #include "prover.h"
+#include <cstdlib>
+#include <thread>
 #include "../../include/ezkvm_prover.h"
 #include "../../include/ezkvm_rescue_constants.h"
 #include "common.h"
@@ -115,6 +117,46 @@ GpuProver::GpuProver(int device) : device_(device) {
     for (auto& e : copy_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
+// The overlap of the trace upload with the first transforms needs page-locked source memory; a drop-in caller
+// (TraceTable's Vec<BaseElement> columns, vm/src/lib.rs:18) has pageable memory, for which cudaMemcpyAsync stages
+// through one driver thread (41 ms for the 448 MiB of a 2^20-row trace, measured).  With EZK_STAGED_UPLOAD=1 such
+// columns go through the prover's own page-locked ring instead.  Opt-in until measured on the GPU box.
+bool GpuProver::use_staged_upload(const uint8_t* const* host_columns) {
+    const char* v = getenv("EZK_STAGED_UPLOAD");  // read per proof: tests switch it inside one process
+    if (!v || v[0] != '1') return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_columns[0]) != cudaSuccess) {
+        cudaGetLastError();  // older drivers report unregistered memory as an error: that is the pageable case
+    } else if (attr.type != cudaMemoryTypeUnregistered) {
+        return false;  // page-locked or managed: the plain asynchronous copy already overlaps
+    }
+    if (!copy_pool_) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        copy_pool_.reset(new CopyPool(std::max(1u, std::min(4u, hw / 2))));
+        if (const char* kb = getenv("EZK_STAGE_SLOT_KB")) {  // tests: small slots => many chunks per column
+            const long k = atol(kb);
+            if (k >= 4 && k <= (long)(kStageSlotBytes >> 10)) stage_slot_bytes_ = (size_t)k << 10;
+        }
+        for (int i = 0; i < kStageSlots; i++) {
+            EZK_CUDA(cudaMallocHost(&stage_[i], kStageSlotBytes));
+            EZK_CUDA(cudaEventCreateWithFlags(&stage_ev_[i], cudaEventDisableTiming));
+        }
+    }
+    return true;
+}
+
+// One column through the ring: slot k is refilled once the copy that last read it has finished.
+void GpuProver::staged_copy_column(uint4* d_dst, const uint8_t* src, size_t bytes, uint64_t& chunk) {
+    for (size_t off = 0; off < bytes; off += stage_slot_bytes_, chunk++) {
+        const size_t len = std::min(stage_slot_bytes_, bytes - off);
+        const int slot = (int)(chunk % kStageSlots);
+        EZK_CUDA(cudaEventSynchronize(stage_ev_[slot]));  // returns at once for an event never recorded
+        copy_pool_->copy(stage_[slot], src + off, len);
+        EZK_CUDA(cudaMemcpyAsync((uint8_t*)d_dst + off, stage_[slot], len, cudaMemcpyHostToDevice, copy_stream_));
+        EZK_CUDA(cudaEventRecord(stage_ev_[slot], copy_stream_));
+    }
+}
+
 void GpuProver::join(int rank, int world, const uint8_t id[128]) {
     EZK_CUDA(cudaSetDevice(device_));
     sync();
@@ -146,6 +188,10 @@ GpuProver::~GpuProver() {
     cudaFree(d_params_);
     cudaFree(d_bden_);
     cudaFreeHost(pinned_);
+    for (int i = 0; i < kStageSlots; i++) {
+        if (stage_ev_[i]) cudaEventDestroy(stage_ev_[i]);
+        if (stage_[i]) cudaFreeHost(stage_[i]);
+    }
     cudaFree(arena_.base);
     ntt_tables_free(tables_);
     cudaStreamDestroy(stream_);
@@ -287,13 +333,20 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
             constexpr uint32_t kGroup = 2;  // small groups: the pipeline fills after 2 columns (32 MiB at 2^20), not 7
             EZK_CUDA(cudaEventRecord(copy_ev_[kWidth / kGroup], stream_));
             EZK_CUDA(cudaStreamWaitEvent(copy_stream_, copy_ev_[kWidth / kGroup], 0));  // the arena may still be in use
-            for (uint32_t g = 0; g < kWidth / kGroup; g++) {
+            const bool staged = use_staged_upload(host_columns);
+            uint64_t chunk = 0;
+            for (uint32_t g = 0; !staged && g < kWidth / kGroup; g++) {
                 for (uint32_t c = g * kGroup; c < (g + 1) * kGroup; c++)
                     EZK_CUDA(cudaMemcpyAsync(d_trace_in + (size_t)c * n, host_columns[c], n * 16, cudaMemcpyHostToDevice,
                                              copy_stream_));
                 EZK_CUDA(cudaEventRecord(copy_ev_[g], copy_stream_));
             }
             for (uint32_t g = 0; g < kWidth / kGroup; g++) {
+                if (staged) {  // this thread feeds the ring, so the transforms of a group are queued as soon as it is sent
+                    for (uint32_t c = g * kGroup; c < (g + 1) * kGroup; c++)
+                        staged_copy_column(d_trace_in + (size_t)c * n, host_columns[c], n * 16, chunk);
+                    EZK_CUDA(cudaEventRecord(copy_ev_[g], copy_stream_));
+                }
                 EZK_CUDA(cudaStreamWaitEvent(stream_, copy_ev_[g], 0));
                 if (g == 0) mark();
                 const size_t c0 = (size_t)g * kGroup;

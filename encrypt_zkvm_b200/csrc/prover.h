@@ -3,8 +3,10 @@
 #pragma once
 #include "air/constraints.cuh"
 #include "dist/comm.h"
+#include "host/copy_pool.h"
 #include "host/transcript.h"
 #include "ntt/ntt.cuh"
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -75,6 +77,16 @@ private:
     Arena arena_;
     uint8_t* pinned_ = nullptr;  // small host staging buffer
     size_t pinned_bytes_ = 0;
+    // Staged trace upload for pageable caller memory (opt-in: EZK_STAGED_UPLOAD=1): a ring of page-locked slots
+    // filled by a few host threads, drained by the copy stream.  Created on first use.
+    static constexpr int kStageSlots = 3;
+    static constexpr size_t kStageSlotBytes = 16u << 20;
+    size_t stage_slot_bytes_ = kStageSlotBytes;
+    uint8_t* stage_[kStageSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev_[kStageSlots] = {nullptr, nullptr, nullptr};
+    std::unique_ptr<CopyPool> copy_pool_;
+    bool use_staged_upload(const uint8_t* const* host_columns);
+    void staged_copy_column(uint4* d_dst, const uint8_t* src, size_t bytes, uint64_t& chunk);
     ConstraintParams* d_params_ = nullptr;
     uint32_t* d_flag_ = nullptr;
     cudaEvent_t ev_[16];
