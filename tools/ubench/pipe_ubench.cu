@@ -1,5 +1,13 @@
 // Issue cost of the integer instructions the f128 arithmetic is made of (cycles per warp-instruction per SM
 // sub-partition), measured with 8 independent accumulators per thread and 8 warps per sub-partition.
+//
+// CHECK THE SASS BEFORE READING A LINE (cuobjdump -sass pipe_ubench | grep -c <mnemonic> per kernel): ptxas rewrites
+// loops whose operands are loop-invariant.  As compiled by nvcc 12.9 the loops of OP 1 (IMAD.WIDE carry pair), 2
+// (IMAD), 4 (IADD3), 5 (IADD3 + IADD3.X / IMAD.X chain) and 9 hold the instructions they name (232 per kernel =
+// 29 x 8), but OP 0's product is hoisted out of the loop (the loop is left with an add pair), and OP 3, 6, 7 and 10
+// are partly folded.  The cost of one IMAD.WIDE.U32 (any carry variant) is therefore the OP 1 figure divided by its
+// two instructions; a 64-bit multiply-accumulate without carries cannot be forced from PTX (with a data-dependent
+// multiplicand ptxas splits it into IMAD.WIDE + IADD3 + IADD3.X).
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -73,7 +81,7 @@ void run(const char* name, int instr_per_op) {
 }
 
 int main() {
-    run<0>("IMAD.WIDE.U32", 1);
+    run<0>("(void: product hoisted, add pair left)", 1);
     run<1>("IMAD.WIDE.U32 carry (x2)", 2);
     run<2>("IMAD (lo)", 1);
     run<3>("IMAD.HI", 1);
