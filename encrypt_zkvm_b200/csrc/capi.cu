@@ -4,9 +4,11 @@
 #include "common.h"
 #include "host/vm.h"
 #include "prover.h"
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 using namespace ezk;
 
@@ -93,6 +95,23 @@ int ezk_device_count(void) {
 }
 uint64_t ezk_kernel_launch_count(void) { return launch_count(); }
 void ezk_free(void* p) { free(p); }
+int ezk_selftest_copy_pool(uint32_t threads, size_t bytes) {
+    return guarded([&] {
+        if (threads == 0 || threads > 64 || bytes > ((size_t)1 << 30)) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad self-test size"};
+        std::vector<uint8_t> src(bytes + 64), dst(bytes + 64);
+        uint64_t x = 0x9E3779B97F4A7C15ULL ^ bytes;
+        for (auto& b : src) b = (uint8_t)((x = x * 6364136223846793005ULL + 1442695040888963407ULL) >> 56);
+        CopyPool pool(threads);
+        const size_t lens[] = {bytes, bytes / 2 + 1, bytes > 4096 ? bytes - 4095 : bytes, 262145 < bytes ? 262145 : bytes, 0};
+        for (size_t len : lens)
+            for (size_t shift : {(size_t)0, (size_t)1, (size_t)63}) {
+                std::fill(dst.begin(), dst.end(), (uint8_t)0xEE);
+                pool.copy(dst.data() + shift, src.data() + shift, len);
+                if (memcmp(dst.data() + shift, src.data() + shift, len) != 0 || dst[shift + len] != 0xEE || (shift && dst[shift - 1] != 0xEE))
+                    throw ProveFailure{EZK_ERR_INTERNAL, "threaded copy differs from memcpy"};
+            }
+    });
+}
 void ezk_default_options(ezk_options* out) {
     if (!out) return;
     out->num_queries = 32, out->blowup_factor = 8, out->grinding_factor = 0, out->field_extension = 1;

@@ -72,6 +72,11 @@ uint64_t ezk_kernel_launch_count(void); /* kernels launched by this library sinc
 void ezk_free(void* p);               /* frees buffers returned by this library */
 void ezk_default_options(ezk_options* out);
 
+/* Host-side self-test of the threaded copy used by the staged trace upload (EZK_STAGED_UPLOAD=1):
+ * copies `bytes` pseudo-random bytes with `threads` threads in chunks of every alignment class and compares.
+ * Needs no GPU.  Returns EZK_OK or EZK_ERR_INTERNAL. */
+int ezk_selftest_copy_pool(uint32_t threads, size_t bytes);
+
 /* ---- prover object: ExecutionProver::new (prover/src/lib.rs:25-37) ---- */
 int ezk_prover_create(int device, ezk_prover** out);
 void ezk_prover_destroy(ezk_prover* p);

@@ -38,6 +38,13 @@ def test_version_and_default_options():
             opt.fri_remainder_max_degree) == (32, 8, 0, 1, 8, 127)
 
 
+@pytest.mark.parametrize("threads", [1, 2, 4, 7])
+def test_threaded_copy_of_the_staged_upload(threads):
+    """csrc/host/copy_pool.h inside the built library: part boundaries, unaligned ends, thread start and stop."""
+    for size in (1, 4096, 300_000, (8 << 20) + 13):
+        assert _lib.lib.ezk_selftest_copy_pool(threads, size) == 0, _lib.lib.ezk_last_error().decode()
+
+
 def test_no_cpu_fallback_without_a_device():
     """On a box without a GPU every compute entry point must fail with EZK_ERR_NO_DEVICE, never compute on the CPU."""
     if ezk.device_count() > 0:
