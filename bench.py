@@ -214,7 +214,7 @@ def main():
     # ---- workload: host VM builds the trace (north star: trace generation stays on the host) ----
     n = 1 << args.log_n
     # EZK_TRACE_CACHE=dir (profiling sessions only) keeps the generated case between invocations: the host VM needs
-    # ~30 s for 2^20 rows, all of it outside the timed regions
+    # 2-3 s for 2^20 rows, all of it outside the timed regions
     seed = parallel.unit_seed(0xE2C0DE00, args.log_n, rank)
     cache = os.environ.get("EZK_TRACE_CACHE")
     cache_file = Path(cache) / f"bench_{args.kind}_{args.log_n}_{seed}.pkl" if cache else None
@@ -398,6 +398,18 @@ def main():
                "sample": f"oracle prove of the same synthetic program at 2^{sample} rows: {secs:.2f} s on 1 thread (the "
                          f"reference runs Winterfell single-threaded); scaled to 2^{args.log_n} rows by n*log2(n)"}
 
+    # ---- informational: the same proofs from PAGEABLE host memory (what a Rust Vec column is), plain and staged
+    # upload, in a subprocess so that nothing it does can touch the contract's numbers above ----
+    pageable = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "tools" / "pageable_e2e.py"), str(args.log_n), str(args.kind),
+                                str(args.steps), str(local_rank)], capture_output=True, text=True, timeout=300)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            pageable = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:
+            pageable = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmups,
         "ms_per_step": t_dev * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -406,7 +418,7 @@ def main():
                 "ms_per_step": t_e2e * 1e3 / args.steps},
         "gpu_launches": launches_total, "clocks": clocks, "roofline": roofline, "int_pipe_roofline": int_pipe, "cpu_baseline": cpu,
         "stages": stages, "kernels": kernels, "proof_bytes": proof_bytes, "sharded_single_proof": sharded,
-        "pipelined": pipelined,
+        "pipelined": pipelined, "pageable_e2e": pageable,
         "hbm_roofline_proofs_per_s": peak * 1e9 / sum(ab.values()),
     }
     print(json.dumps(line), file=out, flush=True)

@@ -1,0 +1,38 @@
+"""End-to-end proofs from a PAGEABLE host trace (what a Rust `Vec<BaseElement>` column is), with the plain upload
+and with the staged upload (EZK_STAGED_UPLOAD=1, csrc/host/copy_pool.h).  Torch-free; prints one JSON line.
+bench.py runs it in a subprocess as the informational `pageable_e2e` key.
+
+    python tools/pageable_e2e.py [log_n] [kind] [steps] [device]
+"""
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import encrypt_zkvm_b200 as ezk
+
+log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+kind = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+device = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+t0 = time.perf_counter()
+prog, ex = ezk.synthetic_case(kind, log_n)
+trace, program_hash, outputs = ex.trace(), prog.hash(), ex.outputs()  # numpy array: pageable memory
+vm_s = time.perf_counter() - t0
+res = {}
+with ezk.ExecutionProver(ezk.ProofOptions(), program_hash, outputs, ezk.ServerKey(), device=device) as p:
+    for mode, name in (("0", "plain"), ("1", "staged")):
+        os.environ["EZK_STAGED_UPLOAD"] = mode
+        for _ in range(2):
+            p.prove(trace)
+        wall = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            proof = p.prove(trace).to_bytes()
+            wall.append((time.perf_counter() - t0) * 1e3)
+        res[name] = {"ms_per_proof": sorted(wall)[len(wall) // 2], "min_ms": min(wall),
+                     "ms_before_first_launch": p.stage_times_ms()["upload"], "proof": proof}
+same = res["plain"].pop("proof") == res["staged"].pop("proof")
+print(json.dumps({"log_n": log_n, "steps": steps, "host_vm_s": vm_s, "identical_bytes": same, **res}), flush=True)
