@@ -119,7 +119,24 @@ def build_oracle(force: bool = False) -> Path:
     return ORACLE_LIB
 
 
+def build_ubench(force: bool = False):
+    """Micro-benchmarks of tools/ubench (stand-alone sm_100a binaries next to their sources; not part of the library)."""
+    out = []
+    for src in sorted((ROOT / "tools" / "ubench").glob("*.cu")):
+        exe = src.with_suffix("")
+        if force or not exe.exists() or exe.stat().st_mtime < src.stat().st_mtime:
+            cmd = [_nvcc(), "-ccbin", _host_cxx(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+                   "-I", str(CSRC), "-o", str(exe), str(src)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
     force = "--force" in sys.argv
     print(build_cuda(force=force, verbose="-v" in sys.argv))
     print(build_oracle(force=force))
+    for exe in build_ubench(force=force):
+        print(exe)
