@@ -410,17 +410,23 @@ def main():
         except Exception as e:
             pageable = {"error": f"{type(e).__name__}: {e}"[:300]}
 
-    # ---- informational: does DFMA issue beside the integer pipes?  A stand-alone micro-benchmark,
-    # a few milliseconds of GPU time after everything above is measured ----
-    fp64_pipe = None
-    exe = ROOT / "tools" / "ubench" / "fp64_pipe_ubench"
-    if world == 1 and not args.no_cpu_baseline and exe.exists():
-        try:
-            r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120,
-                               env={**os.environ, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank))})
-            fp64_pipe = [ln.strip() for ln in r.stdout.splitlines() if ln.strip()] if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
-        except Exception as e:
-            fp64_pipe = {"error": f"{type(e).__name__}: {e}"[:300]}
+    # ---- informational: the stand-alone micro-benchmarks of tools/ubench (integer-pipe issue costs, the f128 product,
+    # and whether DFMA issues beside the integer pipes - DESIGN.md sections 4 and 9); a few milliseconds of GPU time
+    # each, after everything above is measured ----
+    ubench = None
+    if world == 1 and not args.no_cpu_baseline:
+        ubench = {}
+        env = {**os.environ, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank))}
+        for src in sorted((ROOT / "tools" / "ubench").glob("*.cu")):
+            exe = src.with_suffix("")
+            if not exe.exists():
+                continue
+            try:
+                r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120, env=env)
+                ubench[exe.name] = ([ln.strip() for ln in r.stdout.splitlines() if ln.strip()] if r.returncode == 0
+                                    else {"error": (r.stderr or r.stdout)[-300:]})
+            except Exception as e:
+                ubench[exe.name] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmups,
@@ -430,7 +436,7 @@ def main():
                 "ms_per_step": t_e2e * 1e3 / args.steps},
         "gpu_launches": launches_total, "clocks": clocks, "roofline": roofline, "int_pipe_roofline": int_pipe, "cpu_baseline": cpu,
         "stages": stages, "kernels": kernels, "proof_bytes": proof_bytes, "sharded_single_proof": sharded,
-        "pipelined": pipelined, "pageable_e2e": pageable, "ubench_fp64_pipe": fp64_pipe,
+        "pipelined": pipelined, "pageable_e2e": pageable, "ubench": ubench,
         "hbm_roofline_proofs_per_s": peak * 1e9 / sum(ab.values()),
     }
     print(json.dumps(line), file=out, flush=True)
