@@ -132,7 +132,12 @@ bool GpuProver::use_staged_upload(const uint8_t* const* host_columns) {
     }
     if (!copy_pool_) {
         const unsigned hw = std::thread::hardware_concurrency();
-        copy_pool_.reset(new CopyPool(std::max(1u, std::min(4u, hw / 2))));
+        unsigned threads = std::max(1u, std::min(4u, hw / 2));
+        if (const char* t = getenv("EZK_STAGE_THREADS")) {  // measurement knob (tools/pageable_e2e.py)
+            const long k = atol(t);
+            if (k >= 1 && k <= 32) threads = (unsigned)k;
+        }
+        copy_pool_.reset(new CopyPool(threads));
         if (const char* kb = getenv("EZK_STAGE_SLOT_KB")) {  // tests: small slots => many chunks per column
             const long k = atol(kb);
             if (k >= 4 && k <= (long)(kStageSlotBytes >> 10)) stage_slot_bytes_ = (size_t)k << 10;

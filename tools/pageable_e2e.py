@@ -22,9 +22,12 @@ prog, ex = ezk.synthetic_case(kind, log_n)
 trace, program_hash, outputs = ex.trace(), prog.hash(), ex.outputs()  # numpy array: pageable memory
 vm_s = time.perf_counter() - t0
 res = {}
-with ezk.ExecutionProver(ezk.ProofOptions(), program_hash, outputs, ezk.ServerKey(), device=device) as p:
-    for mode, name in (("0", "plain"), ("1", "staged")):
-        os.environ["EZK_STAGED_UPLOAD"] = mode
+
+
+def measure(staged: bool):
+    # a prover of its own per configuration: the copy pool is created on the first staged upload
+    os.environ["EZK_STAGED_UPLOAD"] = "1" if staged else "0"
+    with ezk.ExecutionProver(ezk.ProofOptions(), program_hash, outputs, ezk.ServerKey(), device=device) as p:
         for _ in range(2):
             p.prove(trace)
         wall = []
@@ -32,7 +35,15 @@ with ezk.ExecutionProver(ezk.ProofOptions(), program_hash, outputs, ezk.ServerKe
             t0 = time.perf_counter()
             proof = p.prove(trace).to_bytes()
             wall.append((time.perf_counter() - t0) * 1e3)
-        res[name] = {"ms_per_proof": sorted(wall)[len(wall) // 2], "min_ms": min(wall),
-                     "ms_before_first_launch": p.stage_times_ms()["upload"], "proof": proof}
-same = res["plain"].pop("proof") == res["staged"].pop("proof")
+        return {"ms_per_proof": sorted(wall)[len(wall) // 2], "min_ms": min(wall),
+                "ms_before_first_launch": p.stage_times_ms()["upload"]}, proof
+
+
+res["plain"], want = measure(False)
+same = True
+for threads in (0, 1, 2, 8):  # 0 = the library's default (min(4, cores / 2))
+    if threads:
+        os.environ["EZK_STAGE_THREADS"] = str(threads)
+    res[f"staged_{threads}_threads" if threads else "staged"], got = measure(True)
+    same = same and got == want
 print(json.dumps({"log_n": log_n, "steps": steps, "host_vm_s": vm_s, "identical_bytes": same, **res}), flush=True)
