@@ -230,6 +230,12 @@ def test_lwe_round_trip_and_homomorphic_ops():
 def test_synthetic_programs_have_the_named_lengths_and_valid_traces(oracle):
     """BASELINE.json configs: scalar (1), ciphertext (2), mixed (3) programs padded to 2^k rows."""
     for kind in (1, 2, 3):
+        for log_n in (14, 16):  # every row of the larger traces satisfies the AIR too (oracle's row-by-row check)
+            prog, ex = ezk.synthetic_case(kind, log_n)
+            t = ex.trace()
+            assert t.shape == (28, 1 << log_n, 2) and (1 << (log_n - 2)) <= len(prog) < (1 << (log_n - 1))
+            assert oracle.validate_trace(t, prog.hash() + ex.outputs()) < 0
+    for kind in (1, 2, 3):
         prog, ex = ezk.synthetic_case(kind, 9)
         t = ex.trace()
         assert t.shape == (28, 512, 2)
