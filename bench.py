@@ -428,6 +428,27 @@ def main():
             except Exception as e:
                 ubench[exe.name] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    # ---- informational: experimental build variants (encrypt_zkvm_b200/build.py VARIANTS) against the default build, each
+    # in its own subprocess: same proof bytes?  stage times? ----
+    variants = None
+    if world == 1 and not args.no_cpu_baseline:
+        variants = {}
+        libs = [ROOT / "encrypt_zkvm_b200" / "libezkvm.so"] + sorted((ROOT / "encrypt_zkvm_b200").glob("libezkvm_*.so"))
+        if len(libs) > 1:
+            for lib in libs:
+                try:
+                    r = subprocess.run([sys.executable, str(ROOT / "tools" / "variant_probe.py"), str(args.log_n), str(args.kind),
+                                        "7", str(local_rank)], capture_output=True, text=True, timeout=300,
+                                       env={**os.environ, "EZKVM_LIB": str(lib)})
+                    last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                    variants[lib.name] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-300:]}
+                except Exception as e:
+                    variants[lib.name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            want = variants.get("libezkvm.so", {}).get("proof_sha256")
+            for name, v in variants.items():
+                if "proof_sha256" in v:
+                    v["same_bytes_as_default"] = bool(want) and v["proof_sha256"] == want
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmups,
         "ms_per_step": t_dev * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -436,7 +457,7 @@ def main():
                 "ms_per_step": t_e2e * 1e3 / args.steps},
         "gpu_launches": launches_total, "clocks": clocks, "roofline": roofline, "int_pipe_roofline": int_pipe, "cpu_baseline": cpu,
         "stages": stages, "kernels": kernels, "proof_bytes": proof_bytes, "sharded_single_proof": sharded,
-        "pipelined": pipelined, "pageable_e2e": pageable, "ubench": ubench,
+        "pipelined": pipelined, "pageable_e2e": pageable, "ubench": ubench, "variants": variants,
         "hbm_roofline_proofs_per_s": peak * 1e9 / sum(ab.values()),
     }
     print(json.dumps(line), file=out, flush=True)

@@ -8,8 +8,12 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libezkvm.so"
+# EZKVM_LIB: load another build of the same library instead (experimental build variants of
+# encrypt_zkvm_b200/build.py, compared against the default by tools/variant_probe.py).  Same C ABI, same no-fallback rule.
+LIB_PATH = Path(os.environ["EZKVM_LIB"]) if os.environ.get("EZKVM_LIB") else _PKG / "libezkvm.so"
 
 EZK_OK = 0
 EZK_ERR_INVALID_ARGUMENT = -1
