@@ -104,7 +104,9 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
 # into libezkvm_<name>.so next to the default library.  A variant is never loaded unless EZKVM_LIB points at it
 # (encrypt_zkvm_b200/_lib.py); tools/variant_probe.py compares its proofs and stage times with the default's.
 VARIANTS = {
+    # in-tile NTT twiddles in precomputed form (fe_mul_pre): both passes / the final pass only (ntt/ntt.cu)
     "pretw": {"defines": ["-DEZK_NTT_PRE_TWIDDLES=1"], "sources": ["ntt/ntt.cu"]},
+    "pretwf": {"defines": ["-DEZK_NTT_PRE_TWIDDLES=2"], "sources": ["ntt/ntt.cu"]},
 }
 
 

@@ -57,32 +57,39 @@ __device__ __forceinline__ fe_pre w8_pre() {
 // compact per-size twiddle tables: tw[(1 << k) + e] = w_{2^k}^e, e < 2^k, k <= kTwMaxLog
 constexpr uint32_t kTwMaxLog = 11;
 
-// EZK_NTT_PRE_TWIDDLES=1 (build variant `pretw`, not the default): the compact tables hold every twiddle in
-// precomputed form (4 x 16 bytes: w * 2^(32 i) mod M) and the in-tile twiddle products use fe_mul_pre like the
-// 8-point DFT constants do - 42 instead of 58 instructions per product (79 against 110 cycles in the
-// micro-benchmark) for 4 x the table bytes (256 KiB per direction, L1/L2 resident).
+// EZK_NTT_PRE_TWIDDLES (build variants `pretw` = 1 and `pretwf` = 2, not the default): a second set of compact tables
+// holds every twiddle in precomputed form (4 x 16 bytes: w * 2^(32 i) mod M) and the in-tile twiddle products use
+// fe_mul_pre like the 8-point DFT constants do - 42 instead of 58 instructions per product (79 against 110 cycles in
+// the micro-benchmark) for 4 x the table bytes (256 KiB per direction, L1/L2 resident) and up to 16 instead of 4
+// registers per twiddle in flight.  1: both passes; 2: the final pass only (the strided pass sits at its register
+// limit).  Which passes use them is the Pass type's kPreTw.
 #ifndef EZK_NTT_PRE_TWIDDLES
 #define EZK_NTT_PRE_TWIDDLES 0
 #endif
-#if EZK_NTT_PRE_TWIDDLES
-typedef fe_pre tw_t;
-__device__ __forceinline__ tw_t tw_at(const uint4* __restrict__ tw, uint32_t log_size, uint32_t e) {
-    return fe_pre_ldg(tw + 4 * ((1u << log_size) + e));
-}
-template <class A>
-__device__ __forceinline__ fe mul_tw(A& ar, const fe& x, const tw_t& w) {
-    return ar.mul_pre(x, w);
-}
-#else
-typedef fe tw_t;
-__device__ __forceinline__ tw_t tw_at(const uint4* __restrict__ tw, uint32_t log_size, uint32_t e) {
-    return fe_ldg(tw + (1u << log_size) + e);
-}
-template <class A>
-__device__ __forceinline__ fe mul_tw(A& ar, const fe& x, const tw_t& w) {
-    return ar.mul(x, w);
-}
-#endif
+template <bool PRE>
+struct Tw;
+template <>
+struct Tw<false> {
+    typedef fe type;
+    static __device__ __forceinline__ fe at(const uint4* __restrict__ tw, uint32_t log_size, uint32_t e) {
+        return fe_ldg(tw + (1u << log_size) + e);
+    }
+    template <class A>
+    static __device__ __forceinline__ fe mul(A& ar, const fe& x, const fe& w) {
+        return ar.mul(x, w);
+    }
+};
+template <>
+struct Tw<true> {
+    typedef fe_pre type;
+    static __device__ __forceinline__ fe_pre at(const uint4* __restrict__ tw, uint32_t log_size, uint32_t e) {
+        return fe_pre_ldg(tw + 4 * ((1u << log_size) + e));
+    }
+    template <class A>
+    static __device__ __forceinline__ fe mul(A& ar, const fe& x, const fe_pre& w) {
+        return ar.mul_pre(x, w);
+    }
+};
 
 // b^e from a two-level table with the policy's product (see fe_tab_pow)
 template <class A>
@@ -103,10 +110,10 @@ __device__ __forceinline__ void bf(A& ar, fe& a, fe& b) {
     fe s = ar.add(a, b), d = ar.sub(a, b);
     a = s, b = d;
 }
-template <class A>
-__device__ __forceinline__ void bf_w(A& ar, fe& a, fe& b, const tw_t& w) {
+template <bool PRE, class A>
+__device__ __forceinline__ void bf_w(A& ar, fe& a, fe& b, const typename Tw<PRE>::type& w) {
     fe s = ar.add(a, b), d = ar.sub(a, b);
-    a = s, b = mul_tw(ar, d, w);
+    a = s, b = Tw<PRE>::mul(ar, d, w);
 }
 template <class A>
 __device__ __forceinline__ void bf_pre(A& ar, fe& a, fe& b, const fe_pre& w) {
@@ -151,7 +158,7 @@ __device__ __forceinline__ void dft4(A& ar, fe& m0, fe& m1, fe& m2, fe& m3) {
 // One radix-2^a step (a = 1, 2, 3) of a decimation-in-frequency transform of size 2^log_cur on the 8 registers a
 // thread holds: slot p (p = 0..7) is position q + p * 2^(log_cur-3) of the sub-transform.  On return x[p'] is the
 // value to put back into slot p' (in place), already multiplied by its twiddle w_{2^log_cur}^(q' m').
-template <int INV, class A>
+template <int INV, bool PRE, class A>
 __device__ __forceinline__ void radix_step(A& ar, fe (&x)[8], uint32_t a, uint32_t log_cur, uint32_t q,
                                            const uint4* __restrict__ tw) {
     const uint32_t eighth = 1u << (log_cur - 3);
@@ -159,7 +166,7 @@ __device__ __forceinline__ void radix_step(A& ar, fe (&x)[8], uint32_t a, uint32
         dft8<INV>(ar, x);
         if (log_cur > 3 && q != 0) {
 #pragma unroll
-            for (int k = 1; k < 8; k++) x[k] = mul_tw(ar, x[k], tw_at(tw, log_cur, q * k));
+            for (int k = 1; k < 8; k++) x[k] = Tw<PRE>::mul(ar, x[k], Tw<PRE>::at(tw, log_cur, q * k));
         }
     } else if (a == 2) {
         // two 4-point butterflies: h = p & 1 selects q' = q + h * eighth, m = p >> 1 is the digit
@@ -170,13 +177,13 @@ __device__ __forceinline__ void radix_step(A& ar, fe (&x)[8], uint32_t a, uint32
             const uint32_t qq = q + h * eighth;
             if (qq != 0) {
 #pragma unroll
-                for (int m = 1; m < 4; m++) x[2 * m + h] = mul_tw(ar, x[2 * m + h], tw_at(tw, log_cur, qq * m));
+                for (int m = 1; m < 4; m++) x[2 * m + h] = Tw<PRE>::mul(ar, x[2 * m + h], Tw<PRE>::at(tw, log_cur, qq * m));
             }
         }
     } else {
         // four 2-point butterflies: h = p & 3, digit m = p >> 2 (w^0 = 1 for q' = 0)
 #pragma unroll
-        for (int h = 0; h < 4; h++) bf_w(ar, x[h], x[h + 4], tw_at(tw, log_cur, q + h * eighth));
+        for (int h = 0; h < 4; h++) bf_w<PRE>(ar, x[h], x[h + 4], Tw<PRE>::at(tw, log_cur, q + h * eighth));
     }
 }
 
@@ -217,7 +224,7 @@ __device__ __forceinline__ bool group_compute(const Pass& P, const uint4* tile, 
 #pragma unroll
         for (int p = 0; p < 8; p++) x[p] = fe_load(t0 + p * step);
     }
-    radix_step<INV>(ar, x, c.a, c.log_cur, q, c.tw);
+    radix_step<INV, Pass::kPreTw>(ar, x, c.a, c.log_cur, q, c.tw);
     if (c.last) {
         const typename Pass::Out out = P.begin_out(lane, jg, c.log_s);
 #pragma unroll
@@ -309,6 +316,7 @@ struct StridedPass {
     // carry-free product flag brings (10.43 ms)
     static constexpr bool kLean = false;
     static constexpr int kLeanMul = 0;
+    static constexpr bool kPreTw = EZK_NTT_PRE_TWIDDLES == 1;
     const uint4* src;
     uint4* dst;
     const uint4* roots;
@@ -416,6 +424,7 @@ struct FinalArgs {
 struct FinalPass {
     static constexpr bool kLean = true;
     static constexpr int kLeanMul = 1;
+    static constexpr bool kPreTw = EZK_NTT_PRE_TWIDDLES != 0;
     const FinalArgs* a;
     const uint4* src;   // column base (mode 0, 2) or coset-0 base of this column group (mode 1)
     uint4* dst;
@@ -695,7 +704,7 @@ int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log
         a.log_L = log_L;
         a.inv = inverse ? 1 : 0;
         a.roots = inverse ? t.root_inv : t.root_fwd;
-        a.tw = inverse ? t.tw_inv : t.tw_fwd;
+        a.tw = StridedPass::kPreTw ? (inverse ? t.twp_inv : t.twp_fwd) : (inverse ? t.tw_inv : t.tw_fwd);
         a.big = pass_table(t, s, inverse, a.coset_first != 0, log_stride + a.log_s, log_stride, log_L);
         dim3 grid((unsigned)(((uint64_t)1 << (log_n - pl.log_d[i])) >> a.lanes_log), ncols);
         {
@@ -756,6 +765,8 @@ void ntt_tables_init(NttTables& t) {
     t.off_inv = build(inverse(o));
     std::vector<Fp> cf = build_compact(false), ci = build_compact(true);
     const Fp two32 = Fp::from_u64(1ull << 32);
+    t.tw_fwd = upload(cf);
+    t.tw_inv = upload(ci);
 #if EZK_NTT_PRE_TWIDDLES
     auto expand = [&](const std::vector<Fp>& h) {  // entry j -> w_j * 2^(32 i), i = 0..3
         std::vector<Fp> p(4 * h.size());
@@ -765,11 +776,8 @@ void ntt_tables_init(NttTables& t) {
         }
         return p;
     };
-    t.tw_fwd = upload(expand(cf));
-    t.tw_inv = upload(expand(ci));
-#else
-    t.tw_fwd = upload(cf);
-    t.tw_inv = upload(ci);
+    t.twp_fwd = upload(expand(cf));
+    t.twp_inv = upload(expand(ci));
 #endif
     Fp w8[2][4][4];
     for (int e = 0; e < 4; e++) {
@@ -790,6 +798,7 @@ void ntt_tables_init(NttTables& t) {
 void ntt_tables_free(NttTables& t) {
     cudaFree(t.root_fwd), cudaFree(t.root_inv), cudaFree(t.off_fwd), cudaFree(t.off_inv);
     cudaFree(t.tw_fwd), cudaFree(t.tw_inv);
+    cudaFree(t.twp_fwd), cudaFree(t.twp_inv);
     if (t.big_tables) {
         for (auto& kv : *t.big_tables) cudaFree(kv.second);
         delete t.big_tables;
@@ -836,7 +845,7 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
     if (a.lanes_log > a.log_top) a.lanes_log = a.log_top;
     a.inv = inverse ? 1 : 0;
     a.roots = roots;
-    a.tw = inverse ? t.tw_inv : t.tw_fwd;
+    a.tw = FinalPass::kPreTw ? (inverse ? t.twp_inv : t.twp_fwd) : (inverse ? t.tw_inv : t.tw_fwd);
     a.off_tab = off_tab;
     a.scale = sc;
     a.scale_tab = scale ? scale_table(t, s, log_n, sc) : nullptr;
@@ -868,7 +877,7 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
     a.log_L = log_L;
     a.inv = 0;
     a.roots = t.root_fwd;
-    a.tw = t.tw_fwd;
+    a.tw = FinalPass::kPreTw ? t.twp_fwd : t.tw_fwd;
     a.off_tab = t.off_fwd;
     if (pl.passes == 1) {
         a.mode = 2;

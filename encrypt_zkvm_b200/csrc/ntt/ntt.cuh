@@ -17,6 +17,9 @@ struct NttTables {
     // compact per-size tables: entry (1 << k) + e = w_{2^k}^e (forward) / w_{2^k}^-e (inverse), k <= 11
     uint4* tw_fwd = nullptr;
     uint4* tw_inv = nullptr;
+    // the same tables in precomputed form (4 x 16 bytes per entry); only the experimental EZK_NTT_PRE_TWIDDLES builds fill them
+    uint4* twp_fwd = nullptr;
+    uint4* twp_inv = nullptr;
     // full inter-pass twiddle tables of the strided passes, built on first use per (size, direction) and kept
     // (16 MiB for a plain 2^20 pass, 128 MiB for the 2^20 LDE); sizes above the limit use the two-level tables
     std::map<uint64_t, uint4*>* big_tables = nullptr;
