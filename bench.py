@@ -435,15 +435,18 @@ def main():
         variants = {}
         libs = [ROOT / "encrypt_zkvm_b200" / "libezkvm.so"] + sorted((ROOT / "encrypt_zkvm_b200").glob("libezkvm_*.so"))
         if len(libs) > 1:
-            for lib in libs:
+            # each library with the default NTT launch shape (256 threads x 3 CTAs/SM, <= 80 registers) and with the
+            # 256 x 2 shape (<= 128 registers: no spills for the precomputed-form twiddles)
+            for lib, shape in [(lib, shape) for lib in libs for shape in ("0", "2")]:
+                key = lib.name if shape == "0" else f"{lib.name}@ntt_shape{shape}"
                 try:
                     r = subprocess.run([sys.executable, str(ROOT / "tools" / "variant_probe.py"), str(args.log_n), str(args.kind),
                                         "7", str(local_rank)], capture_output=True, text=True, timeout=300,
-                                       env={**os.environ, "EZKVM_LIB": str(lib)})
+                                       env={**os.environ, "EZKVM_LIB": str(lib), "EZK_NTT_VARIANT": shape})
                     last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-                    variants[lib.name] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-300:]}
+                    variants[key] = json.loads(last[-1]) if r.returncode == 0 and last else {"error": (r.stderr or r.stdout)[-300:]}
                 except Exception as e:
-                    variants[lib.name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                    variants[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
             want = variants.get("libezkvm.so", {}).get("proof_sha256")
             for name, v in variants.items():
                 if "proof_sha256" in v:
