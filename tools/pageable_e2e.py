@@ -46,4 +46,25 @@ for threads in (0, 1, 2, 8):  # 0 = the library's default (min(4, cores / 2))
         os.environ["EZK_STAGE_THREADS"] = str(threads)
     res[f"staged_{threads}_threads" if threads else "staged"], got = measure(True)
     same = same and got == want
+
+# what INTEGRATION.md recommends to callers that prove many traces from the same buffers: page-lock them once
+# (cudaHostRegister) and use the plain upload.  Cost of the registration and the per-proof time after it.
+try:
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    rt.cudaHostRegister.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint]
+    rt.cudaHostUnregister.argtypes = [ctypes.c_void_p]
+    rt.cudaSetDevice(device)
+    t0 = time.perf_counter()
+    rc = rt.cudaHostRegister(trace.ctypes.data, trace.nbytes, 0)
+    reg_ms = (time.perf_counter() - t0) * 1e3
+    if rc == 0:
+        res["registered"], got = measure(False)
+        res["registered"]["cudaHostRegister_ms"] = reg_ms
+        same = same and got == want
+        rt.cudaHostUnregister(trace.ctypes.data)
+    else:
+        res["registered"] = {"error": f"cudaHostRegister returned {rc}"}
+except Exception as e:  # optional datum
+    res["registered"] = {"error": f"{type(e).__name__}: {e}"[:200]}
 print(json.dumps({"log_n": log_n, "steps": steps, "host_vm_s": vm_s, "identical_bytes": same, **res}), flush=True)
