@@ -107,6 +107,8 @@ VARIANTS = {
     # in-tile NTT twiddles in precomputed form (fe_mul_pre): both passes / the final pass only (ntt/ntt.cu)
     "pretw": {"defines": ["-DEZK_NTT_PRE_TWIDDLES=1"], "sources": ["ntt/ntt.cu"]},
     "pretwf": {"defines": ["-DEZK_NTT_PRE_TWIDDLES=2"], "sources": ["ntt/ntt.cu"]},
+    # inter-pass twiddle tables of the strided passes in precomputed form (ntt/ntt.cu)
+    "prepass": {"defines": ["-DEZK_NTT_PRE_PASS_TABLE=1"], "sources": ["ntt/ntt.cu"]},
 }
 
 

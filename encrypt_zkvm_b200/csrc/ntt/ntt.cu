@@ -66,6 +66,14 @@ constexpr uint32_t kTwMaxLog = 11;
 #ifndef EZK_NTT_PRE_TWIDDLES
 #define EZK_NTT_PRE_TWIDDLES 0
 #endif
+// EZK_NTT_PRE_PASS_TABLE=1 (build variant `prepass`, not the default): the full inter-pass twiddle tables of the strided
+// passes hold their entries in precomputed form as well (64 bytes per entry: 512 MiB for the 2^20 LDE), and the output
+// factor of a strided pass becomes a fe_mul_pre.
+#ifndef EZK_NTT_PRE_PASS_TABLE
+#define EZK_NTT_PRE_PASS_TABLE 0
+#endif
+constexpr uint32_t kPassTableWords = EZK_NTT_PRE_PASS_TABLE ? 4 : 1;  // 16-byte words per table entry
+
 template <bool PRE>
 struct Tw;
 template <>
@@ -357,13 +365,17 @@ struct StridedPass {
         const uint64_t at = ((uint64_t)jg << log_stride) + lo0 + lane;
         out.ptr = dst + base - lo0 + at;
         out.step = 1ull << (log_s - 3 + log_stride);
-        out.tab = big ? big + ((uint64_t)coset << log_N) + at : nullptr;
+        out.tab = big ? big + kPassTableWords * (((uint64_t)coset << log_N) + at) : nullptr;
         out.lo = lo0 + lane, out.j0 = jg, out.jstep = 1u << (log_s - 3);
         return out;
     }
     template <class A>
     __device__ __forceinline__ fe finish(A& ar, const Out& out, int p, fe v) const {
+#if EZK_NTT_PRE_PASS_TABLE
+        if (out.tab) return ar.mul_pre(v, fe_pre_ldg(out.tab + 4 * p * out.step));
+#else
         if (out.tab) return ar.mul(v, fe_ldg(out.tab + p * out.step));
+#endif
         const uint64_t ex = (uint64_t)out.lo * (((uint64_t)(out.j0 + p * out.jstep) << (log_L - log_N)) + coset);
         return ex != 0 ? ar.mul(v, root_pow(ar, roots, log_L, ex)) : v;
     }
@@ -626,24 +638,34 @@ __global__ void build_pass_table_kernel(const uint4* __restrict__ roots, uint32_
     if (e >= ((uint64_t)ncosets << log_N)) return;
     const uint64_t c = e >> log_N, idx = e & ((1ull << log_N) - 1);
     const uint64_t j = idx >> log_stride, lo = idx & ((1ull << log_stride) - 1);
+#if EZK_NTT_PRE_PASS_TABLE
+    fe w = fe_root_pow(roots, log_L, lo * ((j << (log_L - log_N)) + c));
+    const fe two32 = fe_make(1ull << 32, 0);
+    for (int i = 0; i < 4; i++) {  // w * 2^(32 i) mod M, canonical
+        fe_store(out + 4 * e + i, w);
+        w = fe_mul(w, two32);
+    }
+#else
     fe_store(out + e, fe_root_pow(roots, log_L, lo * ((j << (log_L - log_N)) + c)));
+#endif
 }
 
 const uint4* pass_table(const NttTables& t, cudaStream_t s, bool inverse, bool coset, uint32_t log_N, uint32_t log_stride,
                         uint32_t log_L) {
     const uint64_t entries = (coset ? 8ull : 1ull) << log_N;
-    if (!t.big_tables || entries * 16 > t.big_table_limit_bytes) return nullptr;
+    const uint64_t table_bytes = entries * 16 * kPassTableWords;
+    if (!t.big_tables || table_bytes > t.big_table_limit_bytes) return nullptr;
     const uint64_t key = ((uint64_t)log_N << 32) | ((uint64_t)log_stride << 16) | ((uint64_t)coset << 1) | (uint64_t)inverse;
     auto it = t.big_tables->find(key);
     if (it != t.big_tables->end()) return it->second;
     uint4* d = nullptr;
-    if (cudaMalloc(&d, entries * 16) != cudaSuccess) {
+    if (cudaMalloc(&d, table_bytes) != cudaSuccess) {
         cudaGetLastError();
         (*t.big_tables)[key] = nullptr;  // not enough memory: keep using the two-level tables
         return nullptr;
     }
     {
-        LaunchScope ls(s, K_NTT_STRIDED, entries * 16);
+        LaunchScope ls(s, K_NTT_STRIDED, table_bytes);
         build_pass_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, s>>>(inverse ? t.root_inv : t.root_fwd, log_N, log_stride,
                                                                                  coset ? log_L : log_N, coset ? 8 : 1, d);
     }
