@@ -56,6 +56,7 @@ SIGNATURES = {
     "ezk_free": (None, [_P]),
     "ezk_default_options": (None, [C.POINTER(EzkOptions)]),
     "ezk_selftest_copy_pool": (C.c_int, [C.c_uint32, C.c_size_t]),
+    "ezk_selftest_host_field": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "ezk_prover_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "ezk_prover_destroy": (None, [_P]),
     "ezk_prover_prove": (C.c_int, [_P, C.POINTER(EzkTrace), C.POINTER(EzkPublicInputs), C.POINTER(EzkOptions),

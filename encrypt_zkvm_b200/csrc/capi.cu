@@ -112,6 +112,20 @@ int ezk_selftest_copy_pool(uint32_t threads, size_t bytes) {
             }
     });
 }
+int ezk_selftest_host_field(const void* a, const void* b, size_t n, void* out4n) {
+    return guarded([&] {
+        if (!a || !b || !out4n) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        const uint8_t *pa = (const uint8_t*)a, *pb = (const uint8_t*)b;
+        uint8_t* po = (uint8_t*)out4n;
+        for (size_t i = 0; i < n; i++) {
+            const Fp x = fp_load(pa + 16 * i), y = fp_load(pb + 16 * i);
+            if (x.v >= Fp::modulus() || y.v >= Fp::modulus()) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "non-canonical element"};
+            Fp r[4];
+            host_field_products(x, y, r[0], r[1], r[2], r[3]);
+            for (int k = 0; k < 4; k++) fp_store(po + 16 * (4 * i + k), r[k]);
+        }
+    });
+}
 void ezk_default_options(ezk_options* out) {
     if (!out) return;
     out->num_queries = 32, out->blowup_factor = 8, out->grinding_factor = 0, out->field_extension = 1;

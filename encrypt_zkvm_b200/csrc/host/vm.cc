@@ -206,6 +206,15 @@ inline size_t pad_to_cycle(size_t len) { return len + (kCycle - (len % kCycle));
 
 }  // namespace
 
+void host_field_products(Fp a, Fp b, Fp& portable, Fp& sponge, Fp& squared, Fp& inv_alpha_power) {
+    portable = a * b;
+    sponge = fmul(a, b);
+    squared = square(a);
+    Fp lanes[4] = {a, b, a + b, a - b};
+    inv_sbox(lanes);
+    inv_alpha_power = lanes[0];
+}
+
 std::string Operation::to_string() const {
     std::string s = op_name(code);
     if (code == OP_PUSH) s += "(" + std::to_string(value) + ")";

@@ -94,6 +94,11 @@ LweKey lwe_keygen(const LweParams& p, uint64_t seed);
 std::vector<Fp> lwe_encrypt(const LweKey& k, uint8_t value, uint64_t seed);
 uint8_t lwe_decrypt(const LweKey& k, const Fp* ciphertext);
 
+// The two host field products side by side, for the self-test of the C ABI (ezk_selftest_host_field): the portable
+// operator* of f128_host.h and the x86-64 block the Rescue sponge uses (identical by construction; checked against
+// big integers in tests/test_host_cpu.py).
+void host_field_products(Fp a, Fp b, Fp& portable, Fp& sponge, Fp& squared, Fp& inv_alpha_power);
+
 struct SplitMix64 {
     uint64_t s;
     explicit SplitMix64(uint64_t seed) : s(seed) {}

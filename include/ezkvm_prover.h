@@ -77,6 +77,12 @@ void ezk_default_options(ezk_options* out);
  * Needs no GPU.  Returns EZK_OK or EZK_ERR_INTERNAL. */
 int ezk_selftest_copy_pool(uint32_t threads, size_t bytes);
 
+/* Host-side self-test of the f128 arithmetic behind the transcript and the VM: for n pairs (a_i, b_i) of canonical
+ * elements writes a_i * b_i (portable product), a_i * b_i (the product the Rescue sponge uses), a_i^2 and
+ * a_i^INV_ALPHA (the sponge's addition chain) - 4 * n elements - for the caller to compare with big integers.
+ * Needs no GPU. */
+int ezk_selftest_host_field(const void* a, const void* b, size_t n, void* out4n);
+
 /* ---- prover object: ExecutionProver::new (prover/src/lib.rs:25-37) ---- */
 int ezk_prover_create(int device, ezk_prover** out);
 void ezk_prover_destroy(ezk_prover* p);

@@ -38,6 +38,28 @@ def test_version_and_default_options():
             opt.fri_remainder_max_degree) == (32, 8, 0, 1, 8, 127)
 
 
+def test_host_field_arithmetic_against_big_integers():
+    """csrc/field/f128_host.h (transcript, per-proof scalars) and the sponge's x86-64 product and addition chain
+    (csrc/host/vm.cc), as compiled into the library: products, squares and x^INV_ALPHA against Python integers."""
+    import random
+    from encrypt_zkvm_b200.prover import array_to_elements, elements_to_array
+    from tests._frames import INV_ALPHA
+    rng = random.Random(0xF128)
+    edge = [0, 1, 2, M - 1, M - 2, 1 << 64, (1 << 64) - 1, 1 << 127, (45 << 40) - 1, 45 << 40, M - (45 << 40), M >> 1, (M >> 1) + 1]
+    a = [x for x in edge for _ in edge] + [rng.randrange(M) for _ in range(3000)]
+    b = [y for _ in edge for y in edge] + [rng.randrange(M) for _ in range(3000)]
+    a += [M - 1 - rng.randrange(1 << 20) for _ in range(500)] + [rng.randrange(1 << rng.randrange(1, 128)) for _ in range(500)]
+    b += [M - 1 - rng.randrange(1 << 20) for _ in range(500)] + [rng.randrange(M) for _ in range(500)]
+    ea, eb = elements_to_array(a), elements_to_array(b)
+    out = np.empty((4 * len(a), 2), dtype=np.uint64)
+    assert _lib.lib.ezk_selftest_host_field(ea.ctypes.data, eb.ctypes.data, len(a), out.ctypes.data) == 0
+    got = array_to_elements(out)
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert got[4 * i] == x * y % M and got[4 * i + 1] == x * y % M, (x, y)
+        assert got[4 * i + 2] == x * x % M, x
+        assert got[4 * i + 3] == pow(x, INV_ALPHA, M), x
+
+
 @pytest.mark.parametrize("threads", [1, 2, 4, 7])
 def test_threaded_copy_of_the_staged_upload(threads):
     """csrc/host/copy_pool.h inside the built library: part boundaries, unaligned ends, thread start and stop."""
