@@ -8,12 +8,9 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-import os
 
 _PKG = Path(__file__).resolve().parent
-# EZKVM_LIB: load another build of the same library instead (experimental build variants of
-# encrypt_zkvm_b200/build.py, compared against the default by tools/variant_probe.py).  Same C ABI, same no-fallback rule.
-LIB_PATH = Path(os.environ["EZKVM_LIB"]) if os.environ.get("EZKVM_LIB") else _PKG / "libezkvm.so"
+LIB_PATH = _PKG / "libezkvm.so"
 
 EZK_OK = 0
 EZK_ERR_INVALID_ARGUMENT = -1
@@ -42,6 +39,11 @@ class EzkPublicInputs(C.Structure):
                 ("lwe_k", C.c_uint32), ("lwe_delta", C.c_uint32)]
 
 
+class EzkWireCompat(C.Structure):
+    _fields_ = [("ood_interleaved", C.c_uint32), ("remainder_low_to_high", C.c_uint32),
+                ("trace_info_aux_rands_byte", C.c_uint32), ("reserved", C.c_uint32), ("first_nonce", C.c_uint64)]
+
+
 class EzkTrace(C.Structure):
     _fields_ = [("columns", C.POINTER(C.c_void_p)), ("width", C.c_uint32), ("length", C.c_uint64)]
 
@@ -55,6 +57,8 @@ SIGNATURES = {
     "ezk_kernel_launch_count": (C.c_uint64, []),
     "ezk_free": (None, [_P]),
     "ezk_default_options": (None, [C.POINTER(EzkOptions)]),
+    "ezk_get_wire_compat": (None, [C.POINTER(EzkWireCompat)]),
+    "ezk_set_wire_compat": (None, [C.POINTER(EzkWireCompat)]),
     "ezk_selftest_copy_pool": (C.c_int, [C.c_uint32, C.c_size_t]),
     "ezk_selftest_host_field": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "ezk_prover_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
@@ -81,6 +85,7 @@ SIGNATURES = {
     "ezk_stage_merkle": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, _P]),
     "ezk_stage_fri_fold": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "ezk_stage_eval_frames": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, _P]),
+    "ezk_stage_eval_frames_sum": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "ezk_stage_ntt": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_int, _P]),
     "ezk_bench_lde_merkle": (C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ezk_bench_fri": (C.c_int, [_P, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),

@@ -100,59 +100,17 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
-# Experimental build variants: the default objects with some translation units recompiled under extra defines, linked
-# into libezkvm_<name>.so next to the default library.  A variant is never loaded unless EZKVM_LIB points at it
-# (encrypt_zkvm_b200/_lib.py); tools/variant_probe.py compares its proofs and stage times with the default's.
-VARIANTS = {
-    # in-tile NTT twiddles in precomputed form (fe_mul_pre): both passes / the final pass only (ntt/ntt.cu)
-    "pretw": {"defines": ["-DEZK_NTT_PRE_TWIDDLES=1"], "sources": ["ntt/ntt.cu"]},
-    "pretwf": {"defines": ["-DEZK_NTT_PRE_TWIDDLES=2"], "sources": ["ntt/ntt.cu"]},
-    # inter-pass twiddle tables of the strided passes in precomputed form (ntt/ntt.cu)
-    "prepass": {"defines": ["-DEZK_NTT_PRE_PASS_TABLE=1"], "sources": ["ntt/ntt.cu"]},
-}
-
-
-def build_variant(name: str, force: bool = False) -> Path:
-    spec = VARIANTS[name]
-    build_cuda()
-    out = PKG / f"libezkvm_{name}.so"
-    vdir = BUILD / name
-    stamp = vdir / "stamp"
-    digest = _digest(_all_inputs()) + " ".join(spec["defines"])
-    if not force and out.exists() and stamp.exists() and stamp.read_text() == digest:
-        return out
-    vdir.mkdir(parents=True, exist_ok=True)
-    nvcc, cxx = _nvcc(), _host_cxx()
-    objs = []
-    for rel in SOURCES:
-        if rel in spec["sources"]:
-            obj = vdir / (rel.replace("/", "_") + ".o")
-            cmd = [nvcc, "-ccbin", cxx, *NVCC_FLAGS, *spec["defines"], "-x", "cu", "-c", str(CSRC / rel), "-o", str(obj)]
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            (vdir / (rel.replace("/", "_") + ".log")).write_text(r.stdout + r.stderr)
-            if r.returncode != 0:
-                raise RuntimeError(f"nvcc failed for {rel} ({name}):\n{r.stdout}\n{r.stderr}")
-        else:
-            obj = BUILD / (rel.replace("/", "_") + ".o")
-        objs.append(obj)
-    cmd = [nvcc, "-ccbin", cxx, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *map(str, objs), "-ldl"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed ({name}):\n{r.stdout}\n{r.stderr}")
-    stamp.write_text(digest)
-    return out
-
-
 def build_oracle(force: bool = False) -> Path:
     """Test infrastructure only: the CPU restatement in oracle/ (never loaded by the product path)."""
-    srcs = [ORACLE_DIR / f for f in ("capi.cpp", "stark.hpp", "air.hpp", "ntt.hpp", "f128.hpp", "blake3.hpp")]
+    srcs = [ORACLE_DIR / f for f in ("capi.cpp", "tracegen.cpp", "stark.hpp", "air.hpp", "ntt.hpp", "f128.hpp", "blake3.hpp")]
     srcs.append(ROOT / "include" / "ezkvm_rescue_constants.h")
+    srcs += [CSRC / "host" / "vm.cc", CSRC / "host" / "vm.h", CSRC / "field" / "f128_host.h"]  # tracegen.cpp's input generator
     stamp = ORACLE_DIR / ".stamp"
     digest = _digest(srcs)
     if not force and ORACLE_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return ORACLE_LIB
     base = [_host_cxx(), "-O3", "-march=x86-64-v3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
-            "-o", str(ORACLE_LIB), str(ORACLE_DIR / "capi.cpp")]
+            "-o", str(ORACLE_LIB), str(ORACLE_DIR / "capi.cpp"), str(ORACLE_DIR / "tracegen.cpp")]
     r = subprocess.run(base + ["-fopenmp"], capture_output=True, text=True)
     if r.returncode != 0:  # OpenMP runtime missing: build single-threaded
         r = subprocess.run(base, capture_output=True, text=True)
@@ -183,5 +141,3 @@ if __name__ == "__main__":
     print(build_oracle(force=force))
     for exe in build_ubench(force=force):
         print(exe)
-    for name in VARIANTS:
-        print(build_variant(name, force=force))

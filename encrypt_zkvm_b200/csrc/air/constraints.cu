@@ -172,6 +172,26 @@ __global__ void frames_kernel(const uint4* cur, const uint4* nxt, const uint4* p
     eval_transition(ar, f, per, reinterpret_cast<const AirConsts*>(p->inv_mds_pre), p->delta, sink);
 }
 
+// the production path of the constraint kernel at frame level: selector-grouped accumulation of sum_j tcoef_j * r_j
+// with the flagged arithmetic and its exact redo (one value per frame)
+__global__ void frames_sum_kernel(const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,
+                                  const ConstraintParams* __restrict__ p, uint4* out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nframes) return;
+    ArrayFrame f{cur + 28 * t, nxt + 28 * t};
+    fe per[9];
+    for (int k = 0; k < 9; k++) per[k] = fe_load(periodic + 9 * t + k);
+    SumSink sink{p, fe_zero()};
+    Arith<true> ar;
+    eval_transition(ar, f, per, reinterpret_cast<const AirConsts*>(p->inv_mds_pre), p->delta, sink);
+    if (ar.tainted()) {
+        Arith<false> exact;
+        sink.acc = fe_zero();
+        eval_transition(exact, f, per, reinterpret_cast<const AirConsts*>(p->inv_mds_pre), p->delta, sink);
+    }
+    fe_store(out + t, sink.acc);
+}
+
 }  // namespace
 
 int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, const uint4* root_inv, uint32_t log_L, const uint64_t a[2],
@@ -207,6 +227,16 @@ int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde
             constraint_kernel<1024, 1, ArithLockstep><<<(unsigned)(L / 1024), 1024, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
         else
             constraint_kernel<128, 4, Arith<true>><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
+    }
+    EZK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+int evaluate_frames_sum(cudaStream_t s, const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,
+                        const ConstraintParams* params, uint4* out) {
+    {
+        LaunchScope ls(s, K_FRAMES, (uint64_t)nframes * 16 * (28 * 2 + 9 + 1));
+        frames_sum_kernel<<<(nframes + 63) / 64, 64, 0, s>>>(cur, nxt, periodic, nframes, params, out);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

@@ -41,4 +41,8 @@ int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde
 int evaluate_frames(cudaStream_t s, const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,
                     const ConstraintParams* params, uint4* out);
 
+// parity helper for the production (selector-grouped, flagged) path: out[f] = sum_j params->tcoef[j] * r_j(frame f)
+int evaluate_frames_sum(cudaStream_t s, const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,
+                        const ConstraintParams* params, uint4* out);
+
 }  // namespace ezk

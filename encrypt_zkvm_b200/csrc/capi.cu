@@ -132,6 +132,21 @@ void ezk_default_options(ezk_options* out) {
     out->fri_folding_factor = 8, out->fri_remainder_max_degree = 127;
 }
 
+void ezk_get_wire_compat(ezk_wire_compat* out) {
+    if (!out) return;
+    const WireCompat& c = wire_compat();
+    out->ood_interleaved = c.ood_interleaved, out->remainder_low_to_high = c.remainder_low_to_high;
+    out->trace_info_aux_rands_byte = c.trace_info_aux_rands_byte, out->reserved = 0, out->first_nonce = c.first_nonce;
+}
+void ezk_set_wire_compat(const ezk_wire_compat* in) {
+    WireCompat c;
+    if (in) {
+        c.ood_interleaved = in->ood_interleaved != 0, c.remainder_low_to_high = in->remainder_low_to_high != 0;
+        c.trace_info_aux_rands_byte = in->trace_info_aux_rands_byte != 0, c.first_nonce = in->first_nonce;
+    }
+    wire_compat() = c;
+}
+
 int ezk_prover_create(int device, ezk_prover** out) {
     return guarded([&] {
         if (!out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "out pointer is null"};
@@ -271,6 +286,16 @@ int ezk_stage_eval_frames(ezk_prover* p, const void* cur, const void* next, cons
         if (!p || !cur || !next || !periodic || !out20 || !nframes) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
         std::lock_guard<std::mutex> lock(p->mu);
         p->impl->stage_eval_frames(cur, next, periodic, nframes, lwe_delta, out20);
+    });
+}
+int ezk_stage_eval_frames_sum(ezk_prover* p, const void* cur, const void* next, const void* periodic, uint32_t nframes,
+                              uint32_t lwe_delta, const void* tcoef20, void* out1) {
+    return guarded([&] {
+        if (!p || !cur || !next || !periodic || !tcoef20 || !out1) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        Fp tc[20];
+        for (int j = 0; j < 20; j++) tc[j] = fp_load(static_cast<const uint8_t*>(tcoef20) + 16 * j);
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->stage_eval_frames_sum(cur, next, periodic, nframes, lwe_delta, tc, out1);
     });
 }
 int ezk_bench_lde_merkle(ezk_prover* p, uint32_t width, uint64_t n, int iters, float* lde_ms, float* merkle_ms) {

@@ -65,13 +65,14 @@ void Comm::init(int rank, int world, const uint8_t idb[128]) {
         api().CommDestroy(static_cast<ncclComm_t>(comm_));
         comm_ = nullptr;
     }
-    rank_ = rank, world_ = world;
+    rank_ = 0, world_ = 1;  // a failed initialisation below leaves a working single-GPU prover
     if (world == 1) return;
     ncclUniqueId id;
     memcpy(&id, idb, 128);
     ncclComm_t c = nullptr;
     check(api().CommInitRank(&c, world, id, rank), "ncclCommInitRank");
     comm_ = c;
+    rank_ = rank, world_ = world;
 }
 
 uint32_t Comm::world_log() const { return world_ == 8 ? 3 : world_ == 4 ? 2 : world_ == 2 ? 1 : 0; }

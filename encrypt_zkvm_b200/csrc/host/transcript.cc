@@ -162,6 +162,11 @@ std::vector<uint64_t> RandomCoin::draw_integers(size_t count, uint64_t domain_si
     return out;
 }
 
+WireCompat& wire_compat() {
+    static WireCompat c;
+    return c;
+}
+
 size_t num_fri_layers(uint64_t lde_size, const ProofOptions& o) {
     const uint64_t max_remainder = (uint64_t)(o.fri_rem_max_deg + 1) * o.blowup;
     size_t layers = 0;

@@ -36,6 +36,18 @@ struct ProofOptions {  // ProofOptions::new(32, 8, 0, FieldExtension::None, 8, 1
     uint32_t num_queries = 32, blowup = 8, grinding = 0, field_ext = 1, fri_fold = 8, fri_rem_max_deg = 127;
 };
 
+// Byte-level details of winter-* 0.9.0 that could not be checked against the crate itself: the
+// proof writer (prover.cu) and the verifier (verifier.cu) read every one of them from this single process-wide
+// struct, which mirrors the test oracle's `Compat` struct field by field, so the first real Winterfell proof can settle
+// them in one place (ezk_set_wire_compat).  Defaults = the current reading of the 0.9.0 sources.
+struct WireCompat {
+    bool ood_interleaved = true;            // A.7: trace states hashed / serialized as [cur_0, next_0, cur_1, next_1, ...]
+    bool remainder_low_to_high = true;      // A.9: FRI remainder coefficients, constant term first
+    bool trace_info_aux_rands_byte = true;  // A.10: TraceInfo carries the aux segment's random-element count (u8)
+    uint64_t first_nonce = 1;               // A.3 (7): the grinding search starts at 1
+};
+WireCompat& wire_compat();
+
 size_t num_fri_layers(uint64_t lde_size, const ProofOptions& o);
 
 // Context::to_elements() ++ PublicInputs::to_elements() (air/src/lib.rs:38-47)

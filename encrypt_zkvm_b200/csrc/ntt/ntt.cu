@@ -57,18 +57,19 @@ __device__ __forceinline__ fe_pre w8_pre() {
 // compact per-size twiddle tables: tw[(1 << k) + e] = w_{2^k}^e, e < 2^k, k <= kTwMaxLog
 constexpr uint32_t kTwMaxLog = 11;
 
-// EZK_NTT_PRE_TWIDDLES (build variants `pretw` = 1 and `pretwf` = 2, not the default): a second set of compact tables
-// holds every twiddle in precomputed form (4 x 16 bytes: w * 2^(32 i) mod M) and the in-tile twiddle products use
-// fe_mul_pre like the 8-point DFT constants do - 42 instead of 58 instructions per product (79 against 110 cycles in
-// the micro-benchmark) for 4 x the table bytes (256 KiB per direction, L1/L2 resident) and up to 16 instead of 4
-// registers per twiddle in flight.  1: both passes; 2: the final pass only (the strided pass sits at its register
-// limit).  Which passes use them is the Pass type's kPreTw.
+// In-tile twiddles in precomputed form: a second set of compact tables holds every twiddle as 4 x 16 bytes
+// (w * 2^(32 i) mod M) and the in-tile twiddle products use fe_mul_pre like the 8-point DFT constants do - 42 instead
+// of 58 instructions per product for 4 x the table bytes (256 KiB per direction, L1/L2 resident) and up to 16 instead
+// of 4 registers per twiddle in flight.  EZK_NTT_PRE_TWIDDLES: 0 off, 1 both passes, 2 the final pass only.  2 is the
+// default: measured on the B200 at 2^20 rows (round-1 end-of-round probes, five proofs each, identical proof bytes)
+// the trace LDE takes 14.1 ms against 15.3-16.5 ms for 0 and 1 - the strided pass sits at its register limit and
+// loses what the shorter product gains.  Which passes use them is the Pass type's kPreTw.
 #ifndef EZK_NTT_PRE_TWIDDLES
-#define EZK_NTT_PRE_TWIDDLES 0
+#define EZK_NTT_PRE_TWIDDLES 2
 #endif
-// EZK_NTT_PRE_PASS_TABLE=1 (build variant `prepass`, not the default): the full inter-pass twiddle tables of the strided
-// passes hold their entries in precomputed form as well (64 bytes per entry: 512 MiB for the 2^20 LDE), and the output
-// factor of a strided pass becomes a fe_mul_pre.
+// EZK_NTT_PRE_PASS_TABLE=1 (measured in round 1, slower: 512 MiB of table traffic for the 2^20 LDE): the full
+// inter-pass twiddle tables of the strided passes hold their entries in precomputed form as well (64 bytes per entry)
+// and the output factor of a strided pass becomes a fe_mul_pre.
 #ifndef EZK_NTT_PRE_PASS_TABLE
 #define EZK_NTT_PRE_PASS_TABLE 0
 #endif

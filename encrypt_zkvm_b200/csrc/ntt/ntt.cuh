@@ -17,7 +17,7 @@ struct NttTables {
     // compact per-size tables: entry (1 << k) + e = w_{2^k}^e (forward) / w_{2^k}^-e (inverse), k <= 11
     uint4* tw_fwd = nullptr;
     uint4* tw_inv = nullptr;
-    // the same tables in precomputed form (4 x 16 bytes per entry); only the experimental EZK_NTT_PRE_TWIDDLES builds fill them
+    // the same tables in precomputed form (4 x 16 bytes per entry), used by the passes whose kPreTw is set (ntt.cu)
     uint4* twp_fwd = nullptr;
     uint4* twp_inv = nullptr;
     // full inter-pass twiddle tables of the strided passes, built on first use per (size, direction) and kept

@@ -119,11 +119,13 @@ GpuProver::GpuProver(int device) : device_(device) {
 
 // The overlap of the trace upload with the first transforms needs page-locked source memory; a drop-in caller
 // (TraceTable's Vec<BaseElement> columns, vm/src/lib.rs:18) has pageable memory, for which cudaMemcpyAsync stages
-// through one driver thread (41 ms for the 448 MiB of a 2^20-row trace, measured).  With EZK_STAGED_UPLOAD=1 such
-// columns go through the prover's own page-locked ring instead.  Opt-in until measured on the GPU box.
+// through one driver thread (41 ms for the 448 MiB of a 2^20-row trace, measured: longer than the proof itself).  Such
+// columns therefore go through the prover's own page-locked ring, filled by a few host threads (copy_pool.h); memory
+// the caller has page-locked (cudaHostRegister / cudaMallocHost) or managed keeps the plain asynchronous copy.
+// EZK_STAGED_UPLOAD=0 switches the ring off (measurement knob).
 bool GpuProver::use_staged_upload(const uint8_t* const* host_columns) {
     const char* v = getenv("EZK_STAGED_UPLOAD");  // read per proof: tests switch it inside one process
-    if (!v || v[0] != '1') return false;
+    if (v && v[0] == '0') return false;
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, host_columns[0]) != cudaSuccess) {
         cudaGetLastError();  // older drivers report unregistered memory as an error: that is the pageable case
@@ -137,15 +139,27 @@ bool GpuProver::use_staged_upload(const uint8_t* const* host_columns) {
             const long k = atol(t);
             if (k >= 1 && k <= 32) threads = (unsigned)k;
         }
-        copy_pool_.reset(new CopyPool(threads));
+        size_t slot_bytes = kStageSlotBytes;
         if (const char* kb = getenv("EZK_STAGE_SLOT_KB")) {  // tests: small slots => many chunks per column
             const long k = atol(kb);
-            if (k >= 4 && k <= (long)(kStageSlotBytes >> 10)) stage_slot_bytes_ = (size_t)k << 10;
+            if (k >= 4 && k <= (long)(kStageSlotBytes >> 10)) slot_bytes = (size_t)k << 10;
         }
+        // the ring and its events first, the pool last: a failed allocation leaves the prover on the plain copy
+        // instead of half-initialised (later proofs would otherwise copy into null slots)
         for (int i = 0; i < kStageSlots; i++) {
-            EZK_CUDA(cudaMallocHost(&stage_[i], kStageSlotBytes));
-            EZK_CUDA(cudaEventCreateWithFlags(&stage_ev_[i], cudaEventDisableTiming));
+            if (!stage_[i] && cudaMallocHost(&stage_[i], kStageSlotBytes) != cudaSuccess) {
+                cudaGetLastError();
+                stage_[i] = nullptr;
+                return false;
+            }
+            if (!stage_ev_[i] && cudaEventCreateWithFlags(&stage_ev_[i], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                stage_ev_[i] = nullptr;
+                return false;
+            }
         }
+        stage_slot_bytes_ = slot_bytes;
+        copy_pool_.reset(new CopyPool(threads));
     }
     return true;
 }
@@ -515,7 +529,12 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         std::copy(host.begin(), host.begin() + 2 * kWidth, ood_trace.begin());
         std::copy(host.begin() + 2 * kWidth, host.end(), ood_comp.begin());
     }
-    coin.reseed(hash_elements(ood_trace.data(), ood_trace.size()));
+    const WireCompat wc = wire_compat();
+    // the frame as it is hashed and serialized: interleaved, or all current states followed by all next states
+    std::vector<Fp> ood_wire = ood_trace;
+    if (!wc.ood_interleaved)
+        for (uint32_t c = 0; c < kWidth; c++) ood_wire[c] = ood_trace[2 * c], ood_wire[kWidth + c] = ood_trace[2 * c + 1];
+    coin.reseed(hash_elements(ood_wire.data(), ood_wire.size()));
     coin.reseed(hash_elements(ood_comp.data(), ood_comp.size()));
     last_.ood_trace = ood_trace, last_.ood_comp = ood_comp;
     {
@@ -590,6 +609,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
             if (!all[i].is_zero())
                 throw ProveFailure{EZK_ERR_DEEP_DEGREE, "FRI remainder has degree >= domain/8: DEEP composition degree too high"};
         remainder.assign(all.begin(), all.begin() + s / 8);
+        if (!wc.remainder_low_to_high) std::reverse(remainder.begin(), remainder.end());
         Hash32 commitment = hash_elements(remainder.data(), remainder.size());
         commitments.insert(commitments.end(), commitment.begin(), commitment.end());
         coin.reseed(commitment);
@@ -599,7 +619,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     mark();
 
     // ---- (6) grinding + query positions ----
-    uint64_t nonce = 1;
+    uint64_t nonce = wc.first_nonce;
     while (coin.leading_zeros(nonce) < opt.grinding) nonce++;
     std::vector<uint64_t> positions = coin.draw_integers(opt.num_queries, L, nonce);
     std::sort(positions.begin(), positions.end());
@@ -609,7 +629,9 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     // ---- (7) openings + serialization ----
     ProofWriter w;
     // TraceInfo: main width, aux width, aux random elements, log2(length), metadata length
-    w.u8((uint8_t)kWidth), w.u8(0), w.u8(0), w.u8((uint8_t)log_n), w.u16(0);
+    w.u8((uint8_t)kWidth), w.u8(0);
+    if (wc.trace_info_aux_rands_byte) w.u8(0);
+    w.u8((uint8_t)log_n), w.u16(0);
     w.u8(16);
     w.element(Fp(Fp::modulus()));
     w.u8((uint8_t)opt.num_queries), w.u8((uint8_t)opt.blowup), w.u8((uint8_t)opt.grinding), w.u8((uint8_t)opt.field_ext);
@@ -699,7 +721,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     // OodFrame
     w.u16((uint16_t)(1 + ood_trace.size() * 16));
     w.u8(2);
-    for (Fp v : ood_trace) w.element(v);
+    for (Fp v : ood_wire) w.element(v);
     w.u16(1), w.u8(0);
     w.u16((uint16_t)(ood_comp.size() * 16));
     for (Fp v : ood_comp) w.element(v);
@@ -825,6 +847,26 @@ void GpuProver::stage_fri_fold(const void* evals, uint64_t s, Fp alpha, void* ne
     put(fc.alpha_oinv, alpha * inverse(Fp::from_u64(kDomainOffset)));
     fri_fold(stream_, tables_.root_inv, d_e, ilog2_u64(s), fc, d_n);
     EZK_CUDA(cudaMemcpyAsync(next_out, d_n, (s / 8) * 16, cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
+
+void GpuProver::stage_eval_frames_sum(const void* cur, const void* nxt, const void* periodic, uint32_t nframes, uint32_t delta,
+                                      const Fp tcoef[20], void* out1) {
+    EZK_CUDA(cudaSetDevice(device_));
+    reserve((size_t)nframes * (28 * 2 + 9 + 1) + 1024);
+    reset_arena();
+    last_ = Last{};
+    uint4 *d_c = alloc(nframes * 28), *d_n = alloc(nframes * 28), *d_p = alloc(nframes * 9), *d_o = alloc(nframes);
+    EZK_CUDA(cudaMemcpyAsync(d_c, cur, (size_t)nframes * 28 * 16, cudaMemcpyHostToDevice, stream_));
+    EZK_CUDA(cudaMemcpyAsync(d_n, nxt, (size_t)nframes * 28 * 16, cudaMemcpyHostToDevice, stream_));
+    EZK_CUDA(cudaMemcpyAsync(d_p, periodic, (size_t)nframes * 9 * 16, cudaMemcpyHostToDevice, stream_));
+    ConstraintParams hp{};
+    hp.delta = delta;
+    for (uint32_t j = 0; j < kTransitions; j++) put(hp.tcoef[j], tcoef[j]), put_pre(hp.tcoef_pre[j], tcoef[j]);
+    for (int i = 0; i < 16; i++) put(hp.inv_mds[i], rescue_const(rescue_inv_mds()[i])), put_pre(hp.inv_mds_pre[i], rescue_const(rescue_inv_mds()[i]));
+    EZK_CUDA(cudaMemcpyAsync(d_params_, &hp, sizeof(hp), cudaMemcpyHostToDevice, stream_));
+    evaluate_frames_sum(stream_, d_c, d_n, d_p, nframes, d_params_, d_o);
+    EZK_CUDA(cudaMemcpyAsync(out1, d_o, (size_t)nframes * 16, cudaMemcpyDeviceToHost, stream_));
     sync();
 }
 

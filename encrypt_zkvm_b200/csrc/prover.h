@@ -53,6 +53,8 @@ public:
     void stage_fri_fold(const void* evals, uint64_t s, Fp alpha, void* next_out);
     void stage_eval_frames(const void* cur, const void* nxt, const void* periodic, uint32_t nframes, uint32_t delta,
                            void* out20);
+    void stage_eval_frames_sum(const void* cur, const void* nxt, const void* periodic, uint32_t nframes, uint32_t delta,
+                               const Fp tcoef[20], void* out1);
     void bench_lde_merkle(uint32_t width, uint64_t n, int iters, float* lde_ms, float* merkle_ms);
     void bench_fri(uint64_t n, int iters, float* fri_ms);
 
@@ -77,7 +79,7 @@ private:
     Arena arena_;
     uint8_t* pinned_ = nullptr;  // small host staging buffer
     size_t pinned_bytes_ = 0;
-    // Staged trace upload for pageable caller memory (opt-in: EZK_STAGED_UPLOAD=1): a ring of page-locked slots
+    // Staged trace upload for pageable caller memory (default; EZK_STAGED_UPLOAD=0 disables): a ring of page-locked slots
     // filled by a few host threads, drained by the copy stream.  Created on first use.
     static constexpr int kStageSlots = 3;
     static constexpr size_t kStageSlotBytes = 16u << 20;

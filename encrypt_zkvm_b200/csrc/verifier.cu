@@ -102,7 +102,8 @@ void GpuProver::verify(const uint8_t* proof, size_t proof_len, const PublicInput
     try {
         Reader r{proof, proof_len};
         // ---- Proof::context ----
-        const uint32_t W = (uint32_t)r.le(1), aux = (uint32_t)r.le(1), aux_rands = (uint32_t)r.le(1);
+        const WireCompat wc = wire_compat();
+        const uint32_t W = (uint32_t)r.le(1), aux = (uint32_t)r.le(1), aux_rands = wc.trace_info_aux_rands_byte ? (uint32_t)r.le(1) : 0;
         const uint32_t log_n = (uint32_t)r.le(1), meta = (uint32_t)r.le(2);
         const uint32_t modlen = (uint32_t)r.le(1);
         const uint8_t* modb = r.bytes(16);
@@ -155,8 +156,13 @@ void GpuProver::verify(const uint8_t* proof, size_t proof_len, const PublicInput
         const uint64_t pow_nonce = r.le(8);
         if (r.le(1) != 0 || !r.ok || r.pos != r.len) throw Reject{"malformed proof tail"};
 
-        std::vector<Fp> ood_cur(kWidth), ood_next(kWidth);  // the frame is serialized interleaved [cur_c, next_c]
-        for (uint32_t c = 0; c < kWidth; c++) ood_cur[c] = ood_states[2 * c], ood_next[c] = ood_states[2 * c + 1];
+        std::vector<Fp> ood_cur(kWidth), ood_next(kWidth);  // serialized interleaved [cur_c, next_c] (WireCompat)
+        for (uint32_t c = 0; c < kWidth; c++) {
+            if (wc.ood_interleaved)
+                ood_cur[c] = ood_states[2 * c], ood_next[c] = ood_states[2 * c + 1];
+            else
+                ood_cur[c] = ood_states[c], ood_next[c] = ood_states[kWidth + c];
+        }
 
         // ---- replay the transcript ----
         RandomCoin coin;
@@ -291,8 +297,10 @@ void GpuProver::verify(const uint8_t* proof, size_t proof_len, const PublicInput
         if (remainder.size() > max_degree_plus_1) throw Reject{"FRI remainder degree is too high"};
         if (hash_elements(remainder.data(), remainder.size()) != commitment(2 + nlayers))
             throw Reject{"FRI remainder does not match its commitment"};
+        std::vector<Fp> rem_poly = remainder;  // the commitment covers the coefficients in wire order
+        if (!wc.remainder_low_to_high) std::reverse(rem_poly.begin(), rem_poly.end());
         for (size_t q = 0; q < pos.size(); q++)
-            if (horner(remainder, o * pow(dg, pos[q])) != evaluations[q]) throw Reject{"FRI remainder is inconsistent with the last layer"};
+            if (horner(rem_poly, o * pow(dg, pos[q])) != evaluations[q]) throw Reject{"FRI remainder is inconsistent with the last layer"};
     } catch (const Reject& e) {
         throw ProveFailure{EZK_ERR_VERIFICATION, std::string("verification failed: ") + e.why};
     } catch (const std::runtime_error& e) {

@@ -277,6 +277,18 @@ class ExecutionProver:
                                         out.ctypes.data))
         return out
 
+    def stage_eval_frames_sum(self, cur: np.ndarray, nxt: np.ndarray, periodic: np.ndarray, delta: int,
+                              tcoef: Sequence[int]) -> np.ndarray:
+        """sum_j tcoef[j] * r_j per frame through the production (grouped, flagged) path of the constraint kernel."""
+        c = np.ascontiguousarray(cur, dtype=np.uint64).reshape(-1, 28, 2)
+        nx = np.ascontiguousarray(nxt, dtype=np.uint64).reshape(-1, 28, 2)
+        p = np.ascontiguousarray(periodic, dtype=np.uint64).reshape(-1, 9, 2)
+        tc = elements_to_array(list(tcoef))
+        out = np.empty((c.shape[0], 2), dtype=np.uint64)
+        check(lib.ezk_stage_eval_frames_sum(self._handle, c.ctypes.data, nx.ctypes.data, p.ctypes.data, c.shape[0], delta,
+                                            tc.ctypes.data, out.ctypes.data))
+        return out
+
     def bench_lde_merkle(self, width: int, n: int, iters: int = 3):
         a, b = C.c_float(), C.c_float()
         check(lib.ezk_bench_lde_merkle(self._handle, width, n, iters, C.byref(a), C.byref(b)))
@@ -294,6 +306,31 @@ def verify(proof, pub_inputs: PublicInputs, min_conjectured_security: int = 95, 
     with ExecutionProver(ProofOptions(), pub_inputs.program_hash, pub_inputs.stack_outputs, pub_inputs.server_key,
                          device=device) as p:
         p.verify(proof, min_conjectured_security)
+
+
+class wire_compat:
+    """Context manager over the process-wide `ezk_wire_compat` switches (byte-level details of the winterfell 0.9.0
+    proof format that only a real reference proof can settle).  Keyword names are the struct's
+    fields: ood_interleaved, remainder_low_to_high, trace_info_aux_rands_byte, first_nonce."""
+
+    def __init__(self, **fields):
+        self._fields = fields
+        self._saved = None
+
+    def __enter__(self):
+        self._saved = _lib.EzkWireCompat()
+        lib.ezk_get_wire_compat(C.byref(self._saved))
+        cur = _lib.EzkWireCompat()
+        lib.ezk_get_wire_compat(C.byref(cur))
+        for k, v in self._fields.items():
+            if k not in dict(_lib.EzkWireCompat._fields_) or k == "reserved":
+                raise ValueError(f"unknown wire-compat switch {k!r}")
+            setattr(cur, k, int(v))
+        lib.ezk_set_wire_compat(C.byref(cur))
+        return self
+
+    def __exit__(self, *exc):
+        lib.ezk_set_wire_compat(C.byref(self._saved))
 
 
 def profile_enable(on: bool) -> None:

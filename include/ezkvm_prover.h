@@ -72,6 +72,20 @@ uint64_t ezk_kernel_launch_count(void); /* kernels launched by this library sinc
 void ezk_free(void* p);               /* frees buffers returned by this library */
 void ezk_default_options(ezk_options* out);
 
+/* Byte-level details of the winterfell 0.9.0 proof format that the reference tree cannot settle (the engine is an
+ * un-vendored dependency).  The proof writer and the verifier both read them from one
+ * process-wide copy of this struct; the defaults are the current reading of the 0.9.0 sources.  Set it before
+ * proving / verifying (not while a proof is in flight).  Mirrors `Compat` of oracle/stark.hpp field by field. */
+typedef struct ezk_wire_compat {
+    uint32_t ood_interleaved;           /* 1: OOD trace states as [cur_0, next_0, cur_1, next_1, ...] (default) */
+    uint32_t remainder_low_to_high;     /* 1: FRI remainder coefficients, constant term first (default) */
+    uint32_t trace_info_aux_rands_byte; /* 1: TraceInfo = u8 width, u8 aux width, u8 aux rands, u8 log2 n, u16 meta (default) */
+    uint32_t reserved;
+    uint64_t first_nonce;               /* where the grinding search starts (default 1) */
+} ezk_wire_compat;
+void ezk_get_wire_compat(ezk_wire_compat* out);
+void ezk_set_wire_compat(const ezk_wire_compat* in); /* NULL restores the defaults */
+
 /* Host-side self-test of the threaded copy used by the staged trace upload (EZK_STAGED_UPLOAD=1):
  * copies `bytes` pseudo-random bytes with `threads` threads in chunks of every alignment class and compares.
  * Needs no GPU.  Returns EZK_OK or EZK_ERR_INTERNAL. */
@@ -174,6 +188,10 @@ int ezk_stage_fri_fold(ezk_prover* p, const void* evals, uint64_t s, const void*
 /* 20 transition-constraint values for explicit frames (reference unit tests: air/src/tests/mod.rs). */
 int ezk_stage_eval_frames(ezk_prover* p, const void* cur, const void* next, const void* periodic, uint32_t nframes,
                           uint32_t lwe_delta, void* out20);
+/* The same frames through the PRODUCTION path of the constraint kernel (selector-grouped accumulation, flagged
+ * arithmetic with its exact redo): out1[f] = sum_j tcoef20[j] * r_j(frame f), one element per frame. */
+int ezk_stage_eval_frames_sum(ezk_prover* p, const void* cur, const void* next, const void* periodic, uint32_t nframes,
+                              uint32_t lwe_delta, const void* tcoef20, void* out1);
 /* Plain transform of column-major `width` x n values; inverse != 0 -> interpolation (scaled by 1/n). */
 int ezk_stage_ntt(ezk_prover* p, const void* columns, uint32_t width, uint64_t n, int inverse, void* out);
 /* Device-resident stage benchmarks for the LDE/Merkle/FRI sweep: run `iters` times on synthetic device data,

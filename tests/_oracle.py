@@ -79,6 +79,8 @@ class Oracle:
         lib.orc_rescue_constants.argtypes = [P, P, P]
         lib.orc_eval_horner.argtypes = [P, C.c_size_t, P, P]
         lib.orc_root_of_unity.argtypes = [C.c_uint, P]
+        lib.orc_synthetic_trace.restype = C.c_int
+        lib.orc_synthetic_trace.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_ulonglong, P, P]
 
     # ---- field ----
     def _bin(self, fn, a, b):
@@ -174,6 +176,16 @@ class Oracle:
         cols = (C.c_void_p * 28)(*[t[c].ctypes.data for c in range(28)])
         pub = to_arr(pub18)
         return int(self.lib.orc_validate_trace(cols, t.shape[1], pub.ctypes.data, lwe_k, delta))
+
+    # ---- input generator of the CPU legs (oracle/tracegen.cpp) ----
+    def synthetic_trace(self, kind: int, log_n: int, seed: int | None = None, delta=16, lwe_k=4):
+        """BASELINE.md's synthetic case built without the product library: (trace (28, n, 2) uint64, pub18 ints)."""
+        seed = 0xE2C0DE00 + log_n if seed is None else seed
+        trace = np.empty((28, 1 << log_n, 2), dtype=np.uint64)
+        pub = np.empty((18, 2), dtype=np.uint64)
+        if self.lib.orc_synthetic_trace(kind, log_n, lwe_k, delta, seed, trace.ctypes.data, pub.ctypes.data) != 0:
+            raise RuntimeError("oracle trace generator failed")
+        return trace, from_arr(pub)
 
     # ---- prover / verifier ----
     def prove(self, trace: np.ndarray, pub18, options: OrcOptions | None = None):

@@ -238,6 +238,68 @@ def test_air_frames_on_gpu_match_oracle(prover, oracle):
             assert _oracle.from_arr(got[k]) == want, f"frame {k}"
 
 
+def test_air_frames_through_the_production_grouped_path(prover, oracle):
+    """The constraint kernel's own path (selector-grouped accumulation, flagged arithmetic + exact redo) at frame
+    level: sum_j c_j r_j per frame against the same sum over the oracle's 20 values, for the reference's unit-test
+    frames and random frames, so that an AIR regression is localised before the `combined` column."""
+    from tests._frames import reference_frames
+    rng = np.random.default_rng(11)
+    frames = reference_frames()
+    cur = [f.cur for f in frames] + [_oracle.from_arr(rand_elems(rng, (28,))) for _ in range(192)]
+    nxt = [f.nxt for f in frames] + [_oracle.from_arr(rand_elems(rng, (28,))) for _ in range(192)]
+    per = [f.periodic for f in frames] + [_oracle.from_arr(rand_elems(rng, (9,))) for _ in range(192)]
+    # random frames with valid op-bit / flag columns as well: selectors 0/1 make single groups survive
+    for k in range(len(frames), len(cur), 2):
+        for c in range(1, 7):
+            cur[k][c] = int(rng.integers(0, 2))
+        per[k][0] = int(rng.integers(0, 2))
+    tcoef = _oracle.from_arr(rand_elems(rng, (20,)))
+    for delta in (16, 4096):
+        got = _oracle.from_arr(prover.stage_eval_frames_sum(np.stack([_oracle.to_arr(c) for c in cur]),
+                                                            np.stack([_oracle.to_arr(c) for c in nxt]),
+                                                            np.stack([_oracle.to_arr(c) for c in per]), delta, tcoef))
+        for k in range(len(cur)):
+            r = oracle.evaluate_transition(cur[k], nxt[k], per[k], delta=delta)
+            want = sum(c * v for c, v in zip(tcoef, r)) % M
+            assert got[k] == want, f"frame {k}"
+        # one coefficient at a time isolates every constraint inside its group
+        for j in range(20):
+            unit = [1 if i == j else 0 for i in range(20)]
+            one = _oracle.from_arr(prover.stage_eval_frames_sum(np.stack([_oracle.to_arr(c) for c in cur[:40]]),
+                                                                np.stack([_oracle.to_arr(c) for c in nxt[:40]]),
+                                                                np.stack([_oracle.to_arr(c) for c in per[:40]]), delta, unit))
+            for k in range(40):
+                assert one[k] == oracle.evaluate_transition(cur[k], nxt[k], per[k], delta=delta)[j], (j, k)
+
+
+@pytest.mark.parametrize("flags", [dict(compat_ood_interleaved=0), dict(compat_remainder_low_to_high=0),
+                                   dict(compat_trace_info_aux_rands_byte=0), dict(compat_first_nonce=0),
+                                   dict(compat_ood_interleaved=0, compat_remainder_low_to_high=0,
+                                        compat_trace_info_aux_rands_byte=0, compat_first_nonce=7)])
+def test_wire_compat_switches_follow_the_oracle(gpu_prover_factory, oracle, flags):
+    """The [V] items of SURVEY App. A.13 sit behind ONE struct in the product (ezk_wire_compat) that mirrors the
+    oracle's compat_* flags: flipped together, writer and verifier of both sides still agree byte for byte; a proof
+    written under one reading is not accepted under another when the reading reaches a hashed or parsed value."""
+    ezk = gpu_prover_factory
+    case = synthetic(2, 10)
+    pub = pub_elements(case.program_hash, case.outputs)
+    oopt = _oracle.default_options(**flags)
+    want = oracle.prove(case.trace, pub, oopt).proof
+    product = {k[len("compat_"):]: v for k, v in flags.items()}
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        default_bytes = p.prove(case.trace).to_bytes()
+        with ezk.wire_compat(**product):
+            got = p.prove(case.trace).to_bytes()
+            p.verify(got)
+            assert oracle.verify(got, pub, oopt) == 0
+        assert got == want
+        assert got != default_bytes
+        assert p.prove(case.trace).to_bytes() == default_bytes  # the switches are restored
+        if set(flags) != {"compat_first_nonce"}:  # any valid nonce verifies: only the search start differs
+            with pytest.raises(ezk.VerifierError):
+                p.verify(got)
+
+
 def test_non_canonical_trace_elements_are_rejected(gpu_prover_factory):
     """`BaseElement` memory is always canonical (< M); bytes that are not must fail loudly, not prove garbage."""
     ezk = gpu_prover_factory

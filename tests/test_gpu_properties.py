@@ -45,6 +45,30 @@ def test_config1_2p16_scalar_program_matches_oracle_bytes(gpu_prover_factory, or
     assert oracle.verify(proof, pub) == 0
 
 
+def test_config2_2p20_ciphertext_program_matches_oracle_bytes(gpu_prover_factory, oracle):
+    """BASELINE.json configs[2], the benchmark's own size: the GPU proof of the 2^20-row ciphertext program equals the
+    CPU oracle's proof byte for byte (the oracle needs ~30 s with OpenMP for it), host and device trace alike."""
+    import torch
+    case = synthetic(2, 20)
+    assert case.trace.shape[1] == 1 << 20
+    pub = case.program_hash + case.outputs
+    oracle.lib.orc_set_num_threads(max(1, oracle.lib.orc_num_threads()))
+    want = oracle.prove(case.trace, pub)
+    ezk = gpu_prover_factory
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, ezk.ServerKey()) as p:
+        proof = p.prove(case.trace).to_bytes()
+        assert p.artifact("trace_root") == want.raw("trace_root"), "trace root"
+        assert p.artifact("constraint_root") == want.raw("comp_root"), "constraint root"
+        assert p.artifact("ood_constraints") == want.raw("ood_comp"), "OOD constraint evaluations"
+        assert p.artifact("fri_roots") == want.raw("fri_roots"), "FRI layer roots"
+        assert p.artifact("remainder") == want.raw("remainder"), "FRI remainder"
+        dev = torch.from_numpy(case.trace.view(np.int64)).cuda()
+        assert p.prove_device(dev.data_ptr(), 1 << 20).to_bytes() == proof
+        p.verify(proof)
+    assert proof == want.proof
+    assert oracle.verify(proof, pub) == 0
+
+
 @pytest.mark.parametrize("kind,log_n", [(2, 18), (3, 19), (2, 20)])
 def test_large_proofs_verify_and_reject_mutations(gpu_prover_factory, oracle, kind, log_n):
     """configs[2] (ciphertext program, 2^20 rows) and two sweep sizes: accepted by the restated verifier."""
@@ -144,7 +168,7 @@ def test_host_and_device_traces_give_identical_bytes_2p18(gpu_prover_factory):
 
 @pytest.mark.parametrize("log_n", [7, 12, 16])
 def test_staged_upload_of_pageable_traces_gives_identical_bytes(gpu_prover_factory, monkeypatch, log_n):
-    """Opt-in upload path for pageable caller memory (EZK_STAGED_UPLOAD=1: page-locked ring filled by host threads,
+    """Default upload path for pageable caller memory (EZK_STAGED_UPLOAD=0 switches it off: page-locked ring filled by host threads,
     csrc/host/copy_pool.h).  Small ring slots make every column travel in several chunks and wrap the ring."""
     ezk = gpu_prover_factory
     case = synthetic(2, log_n)

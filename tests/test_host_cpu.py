@@ -267,3 +267,33 @@ def test_synthetic_programs_have_the_named_lengths_and_valid_traces(oracle):
             assert vm.OPCODES["read2"] not in ops and vm.OPCODES["add"] in ops
         if kind == 2:
             assert vm.OPCODES["read2"] in ops and vm.OPCODES["smul"] in ops and vm.OPCODES["add2"] in ops
+
+
+def test_wire_compat_struct_round_trips_without_a_gpu():
+    """ezk_get/set_wire_compat: defaults are the documented reading; the context manager restores them."""
+    import ctypes as C
+    import encrypt_zkvm_b200 as ezk
+    from encrypt_zkvm_b200 import _lib
+    cur = _lib.EzkWireCompat()
+    _lib.lib.ezk_get_wire_compat(C.byref(cur))
+    assert (cur.ood_interleaved, cur.remainder_low_to_high, cur.trace_info_aux_rands_byte, cur.first_nonce) == (1, 1, 1, 1)
+    with ezk.wire_compat(ood_interleaved=0, first_nonce=5):
+        _lib.lib.ezk_get_wire_compat(C.byref(cur))
+        assert (cur.ood_interleaved, cur.remainder_low_to_high, cur.trace_info_aux_rands_byte, cur.first_nonce) == (0, 1, 1, 5)
+    _lib.lib.ezk_get_wire_compat(C.byref(cur))
+    assert (cur.ood_interleaved, cur.first_nonce) == (1, 1)
+    with pytest.raises(ValueError):
+        with ezk.wire_compat(no_such_switch=1):
+            pass
+    _lib.lib.ezk_set_wire_compat(None)
+
+
+def test_oracle_trace_generator_matches_the_host_vm(oracle):
+    """oracle/tracegen.cpp (input of the CPU legs of bench.py, built without the product library) produces the same
+    trace, program hash and outputs as ezk_synthetic_case."""
+    import encrypt_zkvm_b200 as ezk
+    for kind, log_n in [(1, 8), (2, 10), (3, 12)]:
+        trace, pub = oracle.synthetic_trace(kind, log_n)
+        prog, ex = ezk.synthetic_case(kind, log_n)
+        assert np.array_equal(trace, ex.trace())
+        assert pub == prog.hash() + ex.outputs()

@@ -1,6 +1,7 @@
 """End-to-end proofs from a PAGEABLE host trace (what a Rust `Vec<BaseElement>` column is), with the plain upload
-and with the staged upload (EZK_STAGED_UPLOAD=1, csrc/host/copy_pool.h).  Torch-free; prints one JSON line.
-bench.py runs it in a subprocess as the informational `pageable_e2e` key.
+and with the staged upload (the default for unregistered memory; EZK_STAGED_UPLOAD=0 disables it;
+csrc/host/copy_pool.h), for 1 / 2 / default / 8 copy threads.  Torch-free; prints one JSON line and writes it to
+profiles/r02_pageable_e2e_2p<log_n>.json.
 
     python tools/pageable_e2e.py [log_n] [kind] [steps] [device]
 """
@@ -67,4 +68,6 @@ try:
         res["registered"] = {"error": f"cudaHostRegister returned {rc}"}
 except Exception as e:  # optional datum
     res["registered"] = {"error": f"{type(e).__name__}: {e}"[:200]}
-print(json.dumps({"log_n": log_n, "steps": steps, "host_vm_s": vm_s, "identical_bytes": same, **res}), flush=True)
+line = {"log_n": log_n, "steps": steps, "host_vm_s": vm_s, "identical_bytes": same, **res}
+(Path(__file__).resolve().parent.parent / "profiles" / f"r02_pageable_e2e_2p{log_n}.json").write_text(json.dumps(line, indent=1) + "\n")
+print(json.dumps(line), flush=True)

@@ -1,4 +1,4 @@
-"""Torch-free check of the opt-in staged upload (EZK_STAGED_UPLOAD=1): the proof of a pageable host trace must have
+"""Torch-free check of the staged upload (default for pageable memory; EZK_STAGED_UPLOAD=0 = plain copy): the proof of a pageable host trace must have
 the same bytes with and without it, at sizes with one chunk and with many chunks per column.
 
     python tools/staged_upload_check.py [log_n ...]
