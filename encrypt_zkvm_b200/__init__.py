@@ -8,7 +8,7 @@ import importlib
 
 _EXPORTS = {
     "ExecutionProver": "prover", "LweParameters": "prover", "Proof": "prover", "ProofOptions": "prover",
-    "ProverError": "prover", "VerifierError": "prover", "PublicInputs": "prover", "ServerKey": "prover", "device_count": "prover", "verify": "prover", "wire_compat": "prover",
+    "ProverError": "prover", "VerifierError": "prover", "PublicInputs": "prover", "ServerKey": "prover", "device_count": "prover", "verify": "prover", "wire_compat": "prover", "LocalGroup": "prover", "prove_sharded_in_process": "prover",
     "kernel_launch_count": "prover", "profile_enable": "prover", "profile_reset": "prover", "profile_read": "prover",
     "Execution": "vm", "Program": "vm", "ProgramError": "vm", "ProcessorError": "vm", "ProgramInputs": "vm",
     "execute": "vm", "prove": "vm", "synthetic_case": "vm",

@@ -72,6 +72,9 @@ SIGNATURES = {
     "ezk_prover_verify": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(EzkPublicInputs), C.c_uint32]),
     "ezk_comm_unique_id": (C.c_int, [_P]),
     "ezk_prover_join": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "ezk_local_group_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "ezk_local_group_destroy": (None, [_P]),
+    "ezk_prover_join_local": (C.c_int, [_P, _P, C.c_int]),
     "ezk_prover_stage_times": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "ezk_prover_timer_start": (C.c_int, [_P]),
     "ezk_prover_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float)]),

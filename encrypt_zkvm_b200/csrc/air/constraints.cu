@@ -133,14 +133,18 @@ __global__ void __launch_bounds__(THREADS, MINB) constraint_kernel(const uint4* 
                                                                    uint64_t pitch, uint32_t log_L,
                                                                    const ConstraintParams* __restrict__ p,
                                                                    const uint4* __restrict__ inv_den, RowShard sh,
-                                                                   uint4* __restrict__ combined) {
+                                                                   uint32_t coset_major, uint4* __restrict__ combined) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ((1ull << log_L) >> sh.world_log)) return;
     const uint64_t i = sh.global_row(t);
     fe r;
     if (constraint_row<AR>(roots, lde, pitch, log_L, p, inv_den, t, i, r))
         r = constraint_row_exact(roots, lde, pitch, log_L, p, inv_den, t, i);
-    fe_store(combined + t, r);
+    // packed order (t = rows of this rank in ascending order) or one contiguous array of n values per owned coset
+    // (what the per-coset interpolation of the sharded composition step reads)
+    const uint32_t cn_log = 3 - sh.world_log;
+    const uint64_t at = coset_major ? ((t & ((1u << cn_log) - 1)) << (log_L - 3)) + (t >> cn_log) : t;
+    fe_store(combined + at, r);
 }
 
 struct ArrayFrame {
@@ -209,7 +213,7 @@ int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, const uint4* root
 }
 
 int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde, uint64_t pitch, uint32_t log_L,
-                         const ConstraintParams* params, const uint4* inv_den, uint4* combined, RowShard sh) {
+                         const ConstraintParams* params, const uint4* inv_den, uint4* combined, RowShard sh, bool coset_major) {
     const uint64_t L = (1ull << log_L) >> sh.world_log;
     static int variant = -1;
     if (variant < 0) {
@@ -220,13 +224,13 @@ int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde
         LaunchScope ls(s, K_CONSTRAINTS, L * 16 * (28 + 2));  // 28 columns + inv_den read, 1 column written
         // lockstep variants need full CTAs (every thread reaches every barrier): L is a multiple of 512 for n >= 64
         if (variant == 1 && L % 512 == 0)
-            constraint_kernel<512, 1, ArithLockstep><<<(unsigned)(L / 512), 512, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
+            constraint_kernel<512, 1, ArithLockstep><<<(unsigned)(L / 512), 512, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, coset_major ? 1u : 0u, combined);
         else if (variant == 2 && L % 256 == 0)
-            constraint_kernel<256, 2, ArithLockstep><<<(unsigned)(L / 256), 256, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
+            constraint_kernel<256, 2, ArithLockstep><<<(unsigned)(L / 256), 256, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, coset_major ? 1u : 0u, combined);
         else if (variant == 3 && L % 1024 == 0)
-            constraint_kernel<1024, 1, ArithLockstep><<<(unsigned)(L / 1024), 1024, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
+            constraint_kernel<1024, 1, ArithLockstep><<<(unsigned)(L / 1024), 1024, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, coset_major ? 1u : 0u, combined);
         else
-            constraint_kernel<128, 4, Arith<true>><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, combined);
+            constraint_kernel<128, 4, Arith<true>><<<(unsigned)((L + 127) / 128), 128, 0, s>>>(root_fwd, lde, pitch, log_L, params, inv_den, sh, coset_major ? 1u : 0u, combined);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

@@ -34,8 +34,10 @@ int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, const uint4* root
 
 // combined[i] = T_i / z_t(x_i) + B0_i / (x_i - 1) + B1_i / (x_i - g^(n-2))   
 // lde: column-major 28 x L; inv_den[i] = 1/((x_i - 1)(x_i - g^(n-2)))
+// coset_major: combined[k * n + j] for the k-th coset this rank owns (LDE row 8 j + coset) instead of packed row order
 int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde, uint64_t pitch, uint32_t log_L,
-                         const ConstraintParams* params, const uint4* inv_den, uint4* combined, RowShard sh = RowShard());
+                         const ConstraintParams* params, const uint4* inv_den, uint4* combined, RowShard sh = RowShard(),
+                         bool coset_major = false);
 
 // parity helper: 20 transition values for explicit frames (cur/nxt: nframes x 28, periodic: nframes x 9, out: nframes x 20)
 int evaluate_frames(cudaStream_t s, const uint4* cur, const uint4* nxt, const uint4* periodic, uint32_t nframes,

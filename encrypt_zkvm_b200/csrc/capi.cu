@@ -16,6 +16,9 @@ struct ezk_prover {
     std::unique_ptr<GpuProver> impl;
     std::mutex mu;
 };
+struct ezk_group {
+    std::unique_ptr<LocalGroup> impl;
+};
 struct ezk_program {
     Program prog;
 };
@@ -222,6 +225,22 @@ int ezk_prover_join(ezk_prover* p, int rank, int world, const uint8_t unique_id[
     });
 }
 
+int ezk_local_group_create(int world, ezk_group** out) {
+    return guarded([&] {
+        if (!out) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        auto g = std::make_unique<ezk_group>();
+        g->impl = std::make_unique<LocalGroup>(world);
+        *out = g.release();
+    });
+}
+void ezk_local_group_destroy(ezk_group* g) { delete g; }
+int ezk_prover_join_local(ezk_prover* p, ezk_group* g, int rank) {
+    return guarded([&] {
+        if (!p) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->impl->join_local(rank, g ? g->impl.get() : nullptr);
+    });
+}
 int ezk_prover_timer_start(ezk_prover* p) {
     return guarded([&] {
         if (!p) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};

@@ -132,6 +132,30 @@ __global__ void __launch_bounds__(256) deep_pointwise_kernel(const uint4* __rest
     fe_store(deep + t, fe_mul(num, fe_ldg(inv_den + t)));
 }
 
+// DEEP composition straight from the LDE tables (multi-GPU: everything a rank needs is in the rows it owns):
+// P_i = sum_c dc[c] T_c(x_i), Q_i = sum_j dc[28 + j] H_j(x_i), then the same quotient as deep_pointwise_kernel
+__global__ void __launch_bounds__(256) deep_rows_kernel(const uint4* __restrict__ roots, const uint4* __restrict__ tlde,
+                                                       uint64_t tpitch, const uint4* __restrict__ clde, uint64_t cpitch,
+                                                       uint32_t log_L, const uint4* __restrict__ dc,
+                                                       const uint4* __restrict__ inv_den, DeepScalars sc, RowShard sh,
+                                                       uint4* __restrict__ deep) {
+    const uint64_t L = 1ull << log_L;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (L >> sh.world_log)) return;
+    const uint64_t i = sh.global_row(t);
+    fe P = fe_zero(), Q = fe_zero();
+#pragma unroll 4
+    for (int c = 0; c < 28; c++) P = fe_add(P, fe_mul(fe_ldg(dc + c), fe_ldg(tlde + (uint64_t)c * tpitch + i)));
+#pragma unroll
+    for (int j = 0; j < 7; j++) Q = fe_add(Q, fe_mul(fe_ldg(dc + 28 + j), fe_ldg(clde + (uint64_t)j * cpitch + i)));
+    fe w = fe_root_pow(roots, log_L, i);
+    fe x = fe_add(fe_add(w, w), w);
+    fe t1 = fe_sub(fe_add(P, Q), fe_make(sc.s1[0], sc.s1[1]));
+    fe t2 = fe_sub(P, fe_make(sc.s2[0], sc.s2[1]));
+    fe num = fe_add(fe_mul(t1, fe_sub(x, fe_make(sc.zg[0], sc.zg[1]))), fe_mul(t2, fe_sub(x, fe_make(sc.z[0], sc.z[1]))));
+    fe_store(deep + t, fe_mul(num, fe_ldg(inv_den + t)));
+}
+
 __global__ void all_zero_kernel(const uint4* __restrict__ v, uint64_t count, uint32_t* flag) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t bad = 0;
@@ -203,6 +227,18 @@ int deep_pointwise(cudaStream_t s, const uint4* root_fwd, const uint4* pq_lde, u
     {
         LaunchScope ls(s, K_DEEP_POINTWISE, L * 16 * 4);
         deep_pointwise_kernel<<<(unsigned)((L + 255) / 256), 256, 0, s>>>(root_fwd, pq_lde, log_L, inv_den, sc, sh, deep);
+    }
+    EZK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+int deep_from_rows(cudaStream_t s, const uint4* root_fwd, const uint4* tlde, uint64_t tpitch, const uint4* clde, uint64_t cpitch,
+                   uint32_t log_L, const uint4* deep_coeffs, const uint4* inv_den, DeepScalars sc, uint4* deep, RowShard sh) {
+    const uint64_t rows = (1ull << log_L) >> sh.world_log;
+    {
+        LaunchScope ls(s, K_DEEP_POINTWISE, rows * 16 * (35 + 2));
+        deep_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(root_fwd, tlde, tpitch, clde, cpitch, log_L, deep_coeffs,
+                                                                        inv_den, sc, sh, deep);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

@@ -33,6 +33,13 @@ struct DeepScalars {
 int deep_pointwise(cudaStream_t s, const uint4* root_fwd, const uint4* pq_lde, uint32_t log_L, const uint4* inv_den,
                    DeepScalars sc, uint4* deep, RowShard sh = RowShard());  // multi-GPU: packed rows of this rank
 
+// The same DEEP evaluations from the LDE tables instead of the coefficient tables (the pointwise
+// formula on LDE rows gives identical values): deep[t] for the packed rows t of this rank, reading only rows it owns.
+// Used by the multi-GPU path, where it needs no communication.  tlde: 28 columns, clde: 7 columns (global row index).
+int deep_from_rows(cudaStream_t s, const uint4* root_fwd, const uint4* tlde, uint64_t tpitch, const uint4* clde, uint64_t cpitch,
+                   uint32_t log_L, const uint4* deep_coeffs /* 28 + 7 */, const uint4* inv_den, DeepScalars sc, uint4* deep,
+                   RowShard sh);
+
 // *flag |= 2 when any of the `count` elements is >= M (the kernels assume canonical input, like BaseElement's memory)
 int check_canonical(cudaStream_t s, const uint4* v, uint64_t count, uint32_t* flag);
 

@@ -15,8 +15,10 @@ __device__ __forceinline__ fe ld2(const uint64_t v[2]) { return fe_make(v[0], v[
 // (decimation in frequency, outputs land bit-reversed), Horner in beta = alpha / x_i.
 __global__ void __launch_bounds__(256) fri_fold_kernel(const uint4* __restrict__ root_inv,
                                                       const uint4* __restrict__ evals, uint32_t log_s, FriFoldConsts c,
-                                                      uint4* __restrict__ next) {
-    const uint64_t m = 1ull << (log_s - 3);
+                                                      RowShard sh, uint4* __restrict__ next) {
+    // multi-GPU: `evals` and `next` hold this rank's positions in ascending order (position p = world * t + rank
+    // lives at t), so a row is again 8 values at stride m and only the domain point needs the global index
+    const uint64_t m = (1ull << (log_s - 3)) >> sh.world_log;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     fe a[8];
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const uint4* __restrict__
     }
     // natural order: c_0 = e0, c_1 = e4, c_2 = e2, c_3 = e6, c_4 = e1, c_5 = e5, c_6 = e3, c_7 = e7
     // beta = alpha * x_i^-1 = (alpha/3) * w_s^-i
-    const fe beta = fe_mul(ld2(c.alpha_oinv), fe_root_pow(root_inv, log_s, i));
+    const fe beta = fe_mul(ld2(c.alpha_oinv), fe_root_pow(root_inv, log_s, sh.global_row(i)));
     fe acc = e[7];
     acc = fe_add(fe_mul(acc, beta), e[3]);
     acc = fe_add(fe_mul(acc, beta), e[5]);
@@ -80,11 +82,11 @@ __global__ void fri_remainder_kernel(const uint4* __restrict__ root_inv, const u
 
 }  // namespace
 
-int fri_fold(cudaStream_t s, const uint4* root_inv, const uint4* evals, uint32_t log_s, FriFoldConsts c, uint4* next) {
-    const uint64_t m = 1ull << (log_s - 3);
+int fri_fold(cudaStream_t s, const uint4* root_inv, const uint4* evals, uint32_t log_s, FriFoldConsts c, uint4* next, RowShard sh) {
+    const uint64_t m = (1ull << (log_s - 3)) >> sh.world_log;
     {
         LaunchScope ls(s, K_FRI_FOLD, m * 16 * 9);
-        fri_fold_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(root_inv, evals, log_s, c, next);
+        fri_fold_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(root_inv, evals, log_s, c, sh, next);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "../common.h"
 
 namespace ezk {
 
@@ -14,7 +15,10 @@ struct FriFoldConsts {
 };
 
 // next[i] = sum_k (alpha / x_i)^k * (1/8) sum_j evals[i + j*m] zeta^(-jk),  x_i = 3 w_s^i,  i < m = s/8
-int fri_fold(cudaStream_t s, const uint4* root_inv, const uint4* evals, uint32_t log_s, FriFoldConsts c, uint4* next);
+// multi-GPU (sh): evals / next hold the positions this rank owns (p mod world = rank) in ascending order; log_s is the
+// size of the whole layer
+int fri_fold(cudaStream_t s, const uint4* root_inv, const uint4* evals, uint32_t log_s, FriFoldConsts c, uint4* next,
+             RowShard sh = RowShard());
 
 // coeffs[k] = (1/s) 3^-k sum_i evals[i] w_s^(-ik), k < s (s <= 4096): remainder interpolation over the coset
 int fri_remainder(cudaStream_t s, const uint4* root_inv, const uint4* off_inv, const uint4* evals, uint32_t log_s,

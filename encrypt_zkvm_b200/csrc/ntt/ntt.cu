@@ -557,6 +557,46 @@ __global__ void ntt_tiny_kernel(const uint4* src, uint64_t src_pitch, uint4* dst
     fe_store(dst + (uint64_t)col * dst_pitch + j, acc);
 }
 
+// Composition columns from per-coset interpolations (multi-GPU).  y holds, for each of the 8 LDE cosets c,
+// the plain inverse transform (no 1/n) Y_c of the n constraint evaluations on that coset, as the all-gathered blocks
+// of the ranks: coset c = q + world * k is array (q * (8 / world) + k).  With H'_j[m] = 3^m H_j[m]:
+//     Y_c[m] = n w_L^(cm) sum_j (3^n w_8^c)^j H'_j[m]   =>   H'_j[m] = s_j sum_c w_8^(-cj) w_L^(-cm) Y_c[m],  s_j = 3^(-nj) / L
+// out[j][m] for j < 7; *flag |= 1 when an H'_7[m] is non-zero (composition degree >= 7n).
+struct RecombineConsts {
+    uint64_t s[8][2];
+};
+__global__ void __launch_bounds__(128) composition_recombine_kernel(const uint4* __restrict__ y, uint32_t log_n, uint32_t world_log,
+                                                                   const uint4* __restrict__ root_inv, RecombineConsts k,
+                                                                   uint4* __restrict__ out, uint32_t* __restrict__ flag) {
+    const uint64_t n = 1ull << log_n;
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    Arith<false> ar;
+    const uint32_t cn_log = 3 - world_log;
+    const fe u = fe_root_pow(root_inv, log_n + 3, m);  // w_L^-m
+    fe x[8];
+    fe p = u;
+#pragma unroll
+    for (uint32_t c = 0; c < 8; c++) {
+        const uint32_t q = c & ((1u << world_log) - 1), kk = c >> world_log;
+        fe v = fe_ldg(y + ((uint64_t)((q << cn_log) + kk) << log_n) + m);
+        if (c > 0) {
+            v = fe_mul(v, p);
+            if (c < 7) p = fe_mul(p, u);
+        }
+        x[c] = v;
+    }
+    dft8<1>(ar, x);
+#pragma unroll
+    for (uint32_t j = 0; j < 8; j++) {
+        const fe v = fe_mul(x[j], fe_make(k.s[j][0], k.s[j][1]));
+        if (j < 7)
+            fe_store(out + ((uint64_t)j << log_n) + m, v);
+        else if (!fe_is_zero(v))
+            atomicOr(flag, 1u);
+    }
+}
+
 size_t tile_bytes(uint32_t log_s, uint32_t lanes_log) { return (((size_t)1 << log_s) << lanes_log) * sizeof(uint4); }
 
 struct Plan {
@@ -880,6 +920,19 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
     }
     EZK_CUDA(cudaGetLastError());
     return launches + 1;
+}
+
+int composition_recombine(const NttTables& t, cudaStream_t s, const uint4* y, uint32_t log_n, uint32_t world_log,
+                          const uint64_t scale[8][2], uint4* out, uint32_t* flag) {
+    RecombineConsts k;
+    for (int j = 0; j < 8; j++) k.s[j][0] = scale[j][0], k.s[j][1] = scale[j][1];
+    const uint64_t n = 1ull << log_n;
+    {
+        LaunchScope ls(s, K_NTT_FINAL, n * 16 * 15);
+        composition_recombine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(y, log_n, world_log, t.root_inv, k, out, flag);
+    }
+    EZK_CUDA(cudaGetLastError());
+    return 1;
 }
 
 int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t coeff_pitch, uint4* lde,

@@ -22,6 +22,11 @@ std::atomic<uint64_t> g_launches{0};
 
 constexpr uint32_t kWidth = 28, kCompCols = 7, kTransitions = 20, kAssertions = 22, kCycle = 16, kPeriodic = 9;
 
+inline unsigned ilog2_floor(uint64_t v) {
+    unsigned k = 0;
+    while (v >>= 1) k++;
+    return k;
+}
 inline void put(uint64_t dst[2], Fp v) {
     dst[0] = (uint64_t)v.v;
     dst[1] = (uint64_t)(v.v >> 64);
@@ -105,7 +110,7 @@ GpuProver::GpuProver(int device) : device_(device) {
     EZK_CUDA(cudaSetDevice(device));
     EZK_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     ntt_tables_init(tables_);
-    pinned_bytes_ = 1 << 20;
+    pinned_bytes_ = 8 << 20;  // query openings of every rank of a group (8 x 512 KiB), parameters, small read-backs
     EZK_CUDA(cudaMallocHost(&pinned_, pinned_bytes_));
     EZK_CUDA(cudaMalloc(&d_params_, sizeof(ConstraintParams)));
     EZK_CUDA(cudaMalloc(&d_flag_, sizeof(uint32_t)));
@@ -115,6 +120,7 @@ GpuProver::GpuProver(int device) : device_(device) {
     EZK_CUDA(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
     for (auto& e : aux_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : copy_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : share_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
 // The overlap of the trace upload with the first transforms needs page-locked source memory; a drop-in caller
@@ -182,6 +188,12 @@ void GpuProver::join(int rank, int world, const uint8_t id[128]) {
     comm_.init(rank, world, id);
 }
 
+void GpuProver::join_local(int rank, LocalGroup* group) {
+    EZK_CUDA(cudaSetDevice(device_));
+    sync();
+    comm_.init_local(rank, group);
+}
+
 void GpuProver::timer_start() {
     EZK_CUDA(cudaSetDevice(device_));
     EZK_CUDA(cudaEventRecord(timer_ev_[0], stream_));
@@ -200,6 +212,7 @@ GpuProver::~GpuProver() {
     for (auto& e : ev_) cudaEventDestroy(e);
     for (auto& e : timer_ev_) cudaEventDestroy(e);
     for (auto& e : copy_ev_) cudaEventDestroy(e);
+    for (auto& e : share_ev_) cudaEventDestroy(e);
     cudaStreamDestroy(copy_stream_);
     for (auto& e : aux_ev_) cudaEventDestroy(e);
     cudaStreamDestroy(aux_stream_);
@@ -240,6 +253,16 @@ void GpuProver::sync() { EZK_CUDA(cudaStreamSynchronize(stream_)); }
 
 std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
                                       const PublicInputs& pub, const ProofOptions& opt) {
+    try {
+        return prove_impl(host_columns, device_trace, n, pub, opt);
+    } catch (...) {
+        comm_.abort();  // in-process group: release the peers waiting in a collective
+        throw;
+    }
+}
+
+std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
+                                           const PublicInputs& pub, const ProofOptions& opt) {
     if (opt.field_ext != 1) throw ProveFailure{EZK_ERR_UNSUPPORTED_FIELD_EXTENSION, "only FieldExtension::None is supported"};
     if (opt.blowup != 8 || opt.fri_fold != 8)
         throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "blowup factor and FRI folding factor must both be 8"};
@@ -258,6 +281,21 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     const size_t nlayers = num_fri_layers(L, opt);
     const uint32_t eval_blocks = log_n > 14 ? 1u << (log_n - 14) : 1;
 
+    // ---- multi-GPU layout.  Rank r of G owns the LDE rows i = r mod G (whole cosets: the (i, i + 8) frames
+    // of the constraint evaluation and the 8 points of a FRI row stay on one GPU), interpolates the trace columns
+    // c = r mod G, and holds the Merkle subtree over the leaves [r L / G, (r + 1) L / G) of every commitment.  The
+    // same code runs with G = 1 when EZK_FORCE_SHARDED_PATH=1 (tests: every collective becomes a local copy).
+    const uint32_t G = (uint32_t)comm_.world(), glog = comm_.world_log(), me = (uint32_t)comm_.rank();
+    bool sharded = comm_.active();
+    if (const char* f = getenv("EZK_FORCE_SHARDED_PATH")) sharded = sharded || f[0] == '1';
+    const RowShard sh{me, glog};
+    const CosetSet cs{3 - glog, me, G};
+    const uint32_t cn = 8 / G;                      // cosets per rank
+    const uint64_t L_local = L >> glog;
+    const uint32_t rounds = (kWidth + G - 1) / G;   // trace columns per rank (the last round may be partial)
+    uint64_t shard_fri_min_rows = 4096;             // FRI layers with fewer rows are gathered and finished on every rank
+    if (const char* e = getenv("EZK_SHARD_FRI_MIN_ROWS")) shard_fri_min_rows = std::max<uint64_t>(64, (uint64_t)atoll(e));
+
     // ---- workspace ----
     size_t fri_elems = 0;
     {
@@ -268,51 +306,43 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         }
         fri_elems += 8192;
     }
-    const size_t need = 2 * kWidth * n + 2 * kWidth * L + 4 * L + 3 * L + kCompCols * L + 4 * L + 2 * n + 2 * L + L + 4 * L +
-                        (size_t)(2 * kWidth + kCompCols) * eval_blocks + fri_elems + 65536;
+    const size_t need = 2 * kWidth * n + (sharded ? 4 * n : 0) + 2 * kWidth * L + 4 * L + 3 * L + kCompCols * L + 4 * L + 2 * n + 2 * L + L +
+                        4 * L + (sharded ? 6 * L_local + 16 * n + L + 4096 : 0) + (size_t)(2 * kWidth + kCompCols) * eval_blocks + fri_elems +
+                        4 * 65536;
     reserve(need);
     reset_arena();
     uint4* d_trace_in = host_columns ? alloc(kWidth * n) : nullptr;
-    uint4* d_tcoef = alloc(kWidth * n);
+    uint4* d_tcoef = alloc((size_t)(sharded ? rounds * G : kWidth) * n);
     uint4* d_tlde = alloc(kWidth * L);
     uint4* d_tmp = alloc(kWidth * L);
-    uint4* d_tnodes = alloc(4 * L);
+    uint4* d_tnodes = sharded ? nullptr : alloc(4 * L);
     uint4* d_invden = alloc(L);
     uint4* d_combined = alloc(L);
     uint4* d_ccoef = alloc(L);
     uint4* d_clde = alloc(kCompCols * L);
-    uint4* d_cnodes = alloc(4 * L);
+    uint4* d_cnodes = sharded ? nullptr : alloc(4 * L);
     uint4* d_pq = alloc(2 * n);
-    uint4* d_pqlde = alloc(2 * L);
+    uint4* d_pqlde = sharded ? nullptr : alloc(2 * L);
     uint4* d_deep = alloc(L);
     uint4* d_scratch = alloc((size_t)(2 * kWidth + kCompCols) * eval_blocks);
-    uint4* d_small = alloc(4096);  // OOD outputs, deep coefficients, query staging
-    // multi-GPU: this rank's packed rows (digests or elements) and the all-gathered blocks of every rank
-    const bool sharded = comm_.active();
-    const RowShard sh{(uint32_t)comm_.rank(), comm_.world_log()};
-    const CosetSet cs{3 - comm_.world_log(), (uint32_t)comm_.rank(), (uint32_t)comm_.world()};
-    const uint64_t L_local = L >> comm_.world_log();
+    uint4* d_small = alloc(4096);  // OOD outputs, deep coefficients, subtree roots, flags
+    // sharded: packed per-row products of this rank, the receive side of the exchanges
     uint4* d_pack = sharded ? alloc(2 * L_local) : nullptr;
-    uint4* d_allg = sharded ? alloc(2 * L) : nullptr;
-    // items of `units` 16-byte words per owned row in d_pack -> natural row order in dst, on every rank
-    auto share_rows = [&](uint32_t units, uint4* dst) {
-        comm_.all_gather(d_pack, d_allg, L_local * units * 16, stream_);
-        count_launch();
-        unpack_rows(stream_, d_allg, L_local, comm_.world_log(), units, dst);
+    uint4* d_recv = sharded ? alloc(2 * L_local) : nullptr;
+    uint4* d_rloc = sharded ? alloc((size_t)cn * n) : nullptr;   // per-coset interpolations of the constraint evaluations
+    uint4* d_rall = sharded ? alloc(8 * n) : nullptr;
+    uint4* d_allg = sharded ? alloc(L + 4096) : nullptr;         // gathered FRI evaluations / opened rows of every rank
+
+    struct ShardTree {            // Merkle tree of one commitment
+        bool split = false;       // false: `nodes` is the whole tree (heap order, node 1 = root)
+        uint4* nodes = nullptr;   // split: this rank's subtree over leaves_local leaves (node 1 = subtree root)
+        uint64_t leaves = 0, leaves_local = 0;
+        std::vector<Hash32> top;  // split: heap order, [G, 2G) = subtree roots of the ranks, [1, G) the levels above
     };
-    // leaf digests of a column-major table over the LDE domain -> nodes[L..2L)
-    auto commit_rows = [&](const uint4* table, uint32_t width, uint4* nodes) {
-        if (!sharded) {
-            merkle_hash_rows(stream_, table, L, width, L, nodes);
-        } else {
-            hash_rows_sharded(stream_, table, L, width, L_local, sh, d_pack);
-            share_rows(2, nodes + 2 * L);
-        }
-        merkle_build(stream_, nodes, L);
-    };
+
     last_ = Last{};
-    last_.n = n, last_.L = L, last_.tlde = d_tlde, last_.clde = d_clde, last_.tcoef = d_tcoef;
-    last_.combined_copy = d_combined, last_.deep = d_deep;
+    last_.n = n, last_.L = L, last_.tcoef = d_tcoef;
+    if (!sharded) last_.tlde = d_tlde, last_.clde = d_clde, last_.combined_copy = d_combined, last_.deep = d_deep;
 
     int evi = 0;
     auto mark = [&]() { EZK_CUDA(cudaEventRecord(ev_[evi++], stream_)); };
@@ -328,10 +358,34 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         memcpy(pinned_, src, bytes);
         EZK_CUDA(cudaMemcpyAsync(dst, pinned_, bytes, cudaMemcpyHostToDevice, stream_));
     };
-    auto root_of = [&](const uint4* nodes) {
-        Hash32 r;
-        d2h(r.data(), nodes + 2, 32);  // node 1
-        return r;
+    // commitment to a column-major table over the LDE domain (or to packed digests already in d_pack, table == nullptr)
+    auto commit = [&](const uint4* table, uint32_t width, uint64_t leaves, uint4* whole_nodes, ShardTree& tree) -> Hash32 {
+        Hash32 root;
+        tree.leaves = leaves;
+        if (!sharded) {
+            tree.split = false, tree.nodes = whole_nodes, tree.leaves_local = leaves;
+            merkle_hash_rows(stream_, table, leaves, width, leaves, whole_nodes);
+            merkle_build(stream_, whole_nodes, leaves);
+            d2h(root.data(), whole_nodes + 2, 32);  // node 1
+            return root;
+        }
+        const uint64_t ll = leaves >> glog;  // leaves of this rank's subtree
+        if (table) hash_rows_sharded(stream_, table, leaves, width, ll, sh, d_pack);
+        // rank r's packed digests are those of rows r, r + G, ...: chunk q of them lies in rank q's leaf range
+        tree.split = true, tree.leaves_local = ll, tree.nodes = alloc(4 * ll);
+        comm_.all_to_all(d_pack, d_recv, (ll >> glog) * 32, stream_);
+        count_launch();
+        unpack_rows(stream_, d_recv, ll >> glog, glog, 2, tree.nodes + 2 * ll);
+        merkle_build(stream_, tree.nodes, ll);
+        uint4* d_roots = d_small + 1024;
+        comm_.all_gather(tree.nodes + 2, d_roots, 32, stream_);  // the G subtree roots
+        count_launch();
+        std::vector<Hash32> roots(G);
+        d2h(roots.data(), d_roots, 32 * G);
+        tree.top.assign(2 * G, Hash32{});
+        for (uint32_t q = 0; q < G; q++) tree.top[G + q] = roots[q];
+        for (uint32_t k = G - 1; k >= 1; k--) tree.top[k] = merge_digests(tree.top[2 * k], tree.top[2 * k + 1]);
+        return tree.top[1];
     };
 
     // ---- (0) transcript ----
@@ -346,7 +400,47 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         NttScale sc{};
         put(sc.cvec[0], inverse(Fp::from_u64(n)));
         sc.chunk_shift = 63, sc.use_offset = 1;
-        if (host_columns) {
+        if (sharded) {
+            // this rank interpolates the columns c = me, me + G, ... (uploading only those), round j of every rank is
+            // all-gathered in place into columns [jG, jG + G) on the auxiliary stream, and the extension of a round's
+            // columns over this rank's cosets starts as soon as the round has arrived
+            EZK_CUDA(cudaEventRecord(copy_ev_[15], stream_));
+            EZK_CUDA(cudaStreamWaitEvent(copy_stream_, copy_ev_[15], 0));  // the arena may still be in use
+            EZK_CUDA(cudaStreamWaitEvent(aux_stream_, copy_ev_[15], 0));
+            const bool staged = host_columns && use_staged_upload(host_columns);
+            uint64_t chunk = 0;
+            bool first = true;
+            for (uint32_t j = 0; j < rounds; j++) {
+                const uint32_t c = j * G + me;
+                if (c < kWidth) {
+                    const uint4* src = device_trace ? device_trace + (size_t)c * n : d_trace_in + (size_t)c * n;
+                    if (host_columns) {
+                        if (staged)
+                            staged_copy_column(d_trace_in + (size_t)c * n, host_columns[c], n * 16, chunk);
+                        else
+                            EZK_CUDA(cudaMemcpyAsync(d_trace_in + (size_t)c * n, host_columns[c], n * 16, cudaMemcpyHostToDevice, copy_stream_));
+                        EZK_CUDA(cudaEventRecord(copy_ev_[j % 14], copy_stream_));
+                        EZK_CUDA(cudaStreamWaitEvent(stream_, copy_ev_[j % 14], 0));
+                    }
+                    if (first) mark(), first = false;
+                    check_canonical(stream_, src, n, d_flag_);
+                    ntt_columns(tables_, stream_, src, n, d_tcoef + (size_t)c * n, n, d_tmp, 1, log_n, true, &sc);
+                } else if (first) {
+                    mark(), first = false;
+                }
+                EZK_CUDA(cudaEventRecord(share_ev_[2 * j], stream_));
+                EZK_CUDA(cudaStreamWaitEvent(aux_stream_, share_ev_[2 * j], 0));
+                comm_.all_gather(d_tcoef + (size_t)c * n, d_tcoef + (size_t)j * G * n, n * 16, aux_stream_);
+                count_launch();
+                EZK_CUDA(cudaEventRecord(share_ev_[2 * j + 1], aux_stream_));
+            }
+            for (uint32_t j = 0; j < rounds; j++) {
+                EZK_CUDA(cudaStreamWaitEvent(stream_, share_ev_[2 * j + 1], 0));
+                const size_t c0 = (size_t)j * G;
+                const uint32_t cols = std::min<uint32_t>(G, kWidth - (uint32_t)c0);
+                lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L, L, d_tmp, cols, log_n, cs);
+            }
+        } else if (host_columns) {
             // Upload and transform in column groups: the copy of group k+1 (copy stream) overlaps the
             // interpolation + LDE of group k (compute stream).  Columns are independent until the row hash.
             constexpr uint32_t kGroup = 2;  // small groups: the pipeline fills after 2 columns (32 MiB at 2^20), not 7
@@ -409,8 +503,8 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         EZK_CUDA(cudaEventRecord(aux_ev_[1], aux_stream_));
         d_bden = target;
     }
-    commit_rows(d_tlde, kWidth, d_tnodes);
-    last_.trace_root = root_of(d_tnodes);
+    ShardTree trace_tree, comp_tree;
+    last_.trace_root = commit(d_tlde, kWidth, L, d_tnodes, trace_tree);
     commitments.insert(commitments.end(), last_.trace_root.begin(), last_.trace_root.end());
     coin.reseed(last_.trace_root);
     mark();
@@ -471,33 +565,50 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         for (uint32_t k = 0; k < 128 * kPeriodic; k++) put(hp.ptable[k], ptable_[k]);
         h2d(d_params_, &hp, sizeof(hp));
         EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[1], 0));
-        evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_bden, sharded ? d_pack : d_combined, sh);
-        if (sharded) share_rows(1, d_combined);
+        // sharded: one contiguous array per owned coset, which is what the per-coset interpolation below reads
+        evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_bden, d_combined, sh, sharded);
     }
     mark();
 
     // ---- (3) composition polynomial: interpolate over the coset, 7 columns of n, LDE, commitment ----
     {
-        NttScale sc{};
         const Fp l_inv = inverse(Fp::from_u64(L)), o_n_inv = pow(o_inv, n);
+        uint64_t scale8[8][2];
         Fp acc = l_inv;
         for (int j = 0; j < 8; j++) {
-            put(sc.cvec[j], acc);  // 3^(-jn) / L
+            put(scale8[j], acc);  // 3^(-jn) / L
             acc = acc * o_n_inv;
         }
-        sc.chunk_shift = log_n, sc.use_offset = 0;
-        ntt_columns(tables_, stream_, d_combined, L, d_ccoef, L, d_tmp, 1, log_L, true, &sc);
-        check_all_zero(stream_, d_ccoef + 7 * n, n, d_flag_);
         uint32_t flag = 0;
-        d2h(&flag, d_flag_, sizeof(flag));
+        if (sharded) {
+            // C(x) = sum_j x^(jn) H_j(x) restricted to coset c is R_c(x) = sum_j (3^n w_8^c)^j H_j(x), degree < n: every
+            // rank interpolates its cosets, the 8 coefficient arrays are all-gathered, and an 8-point inverse DFT across
+            // the cosets separates the H_j (see composition_recombine_kernel)
+            ntt_columns(tables_, stream_, d_combined, n, d_rloc, n, d_tmp, cn, log_n, true, nullptr);
+            comm_.all_gather(d_rloc, d_rall, (size_t)cn * n * 16, stream_);
+            count_launch();
+            composition_recombine(tables_, stream_, d_rall, log_n, glog, scale8, d_ccoef, d_flag_);
+            uint32_t* d_flags = reinterpret_cast<uint32_t*>(d_small + 2048);
+            comm_.all_gather(d_flag_, d_flags, sizeof(uint32_t), stream_);  // every rank takes the same decision
+            count_launch();
+            uint32_t flags[8] = {0};
+            d2h(flags, d_flags, sizeof(uint32_t) * G);
+            for (uint32_t q = 0; q < G; q++) flag |= flags[q];
+        } else {
+            NttScale sc{};
+            memcpy(sc.cvec, scale8, sizeof(scale8));
+            sc.chunk_shift = log_n, sc.use_offset = 0;
+            ntt_columns(tables_, stream_, d_combined, L, d_ccoef, L, d_tmp, 1, log_L, true, &sc);
+            check_all_zero(stream_, d_ccoef + 7 * n, n, d_flag_);
+            d2h(&flag, d_flag_, sizeof(flag));
+        }
         if (flag & 2)
             throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "the trace contains non-canonical field elements (values >= the modulus)"};
         if (flag)
             throw ProveFailure{EZK_ERR_CONSTRAINT_DEGREE,
                                "constraint composition polynomial has degree >= 7n: the trace does not satisfy the AIR"};
         lde_columns(tables_, stream_, d_ccoef, n, d_clde, L, d_tmp, kCompCols, log_n, cs);
-        commit_rows(d_clde, kCompCols, d_cnodes);
-        last_.comp_root = root_of(d_cnodes);
+        last_.comp_root = commit(d_clde, kCompCols, L, d_cnodes, comp_tree);
         commitments.insert(commitments.end(), last_.comp_root.begin(), last_.comp_root.end());
         coin.reseed(last_.comp_root);
     }
@@ -522,12 +633,31 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         }
         // powers of the two points once (d_pq is free until the DEEP combination), then 63 dot products
         power_table(stream_, log_n, y, 2, d_pq);
-        eval_polys(stream_, d_tcoef, n, kWidth, log_n, d_pq, 2, d_scratch, d_ood);
-        eval_polys(stream_, d_ccoef, n, kCompCols, log_n, d_pq, 1, d_scratch + (size_t)2 * kWidth * eval_blocks, d_ood + 2 * kWidth);
-        std::vector<Fp> host(2 * kWidth + kCompCols);
-        d2h(host.data(), d_ood, host.size() * 16);
-        std::copy(host.begin(), host.begin() + 2 * kWidth, ood_trace.begin());
-        std::copy(host.begin() + 2 * kWidth, host.end(), ood_comp.begin());
+        if (sharded) {
+            // rank r evaluates the trace columns c = r mod G and the composition columns j = r mod G; the blocks of
+            // 2 * rounds + ceil(7 / G) values are all-gathered
+            const uint32_t cr = (kCompCols + G - 1) / G, block = 2 * rounds + cr;
+            const uint32_t mine_t = me < kWidth ? (kWidth - me + G - 1) / G : 0, mine_c = me < kCompCols ? (kCompCols - me + G - 1) / G : 0;
+            if (mine_t) eval_polys(stream_, d_tcoef + (size_t)me * n, (uint64_t)G * n, mine_t, log_n, d_pq, 2, d_scratch, d_ood);
+            if (mine_c)
+                eval_polys(stream_, d_ccoef + (size_t)me * n, (uint64_t)G * n, mine_c, log_n, d_pq, 1,
+                           d_scratch + (size_t)2 * kWidth * eval_blocks, d_ood + 2 * rounds);
+            uint4* d_ood_all = d_small + 128;
+            comm_.all_gather(d_ood, d_ood_all, (size_t)block * 16, stream_);
+            count_launch();
+            std::vector<Fp> host((size_t)block * G);
+            d2h(host.data(), d_ood_all, host.size() * 16);
+            for (uint32_t c = 0; c < kWidth; c++)
+                for (uint32_t k = 0; k < 2; k++) ood_trace[2 * c + k] = host[(size_t)(c % G) * block + 2 * (c / G) + k];
+            for (uint32_t j = 0; j < kCompCols; j++) ood_comp[j] = host[(size_t)(j % G) * block + 2 * rounds + j / G];
+        } else {
+            eval_polys(stream_, d_tcoef, n, kWidth, log_n, d_pq, 2, d_scratch, d_ood);
+            eval_polys(stream_, d_ccoef, n, kCompCols, log_n, d_pq, 1, d_scratch + (size_t)2 * kWidth * eval_blocks, d_ood + 2 * kWidth);
+            std::vector<Fp> host(2 * kWidth + kCompCols);
+            d2h(host.data(), d_ood, host.size() * 16);
+            std::copy(host.begin(), host.begin() + 2 * kWidth, ood_trace.begin());
+            std::copy(host.begin() + 2 * kWidth, host.end(), ood_comp.begin());
+        }
     }
     const WireCompat wc = wire_compat();
     // the frame as it is hashed and serialized: interleaved, or all current states followed by all next states
@@ -537,6 +667,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     coin.reseed(hash_elements(ood_wire.data(), ood_wire.size()));
     coin.reseed(hash_elements(ood_comp.data(), ood_comp.size()));
     last_.ood_trace = ood_trace, last_.ood_comp = ood_comp;
+    uint4* d_deep_local = d_deep;  // sharded: this rank's DEEP evaluations in packed row order (L / G of them)
     {
         std::vector<Fp> dc(kWidth + kCompCols);
         for (auto& v : dc) v = coin.draw();
@@ -546,29 +677,45 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
             s2 = s2 + dc[c] * ood_trace[2 * c + 1];
         }
         for (uint32_t j = 0; j < kCompCols; j++) s1 = s1 + dc[kWidth + j] * ood_comp[j];
-        uint4* d_dc = d_small + 128;
+        uint4* d_dc = d_small + 512;
         h2d(d_dc, dc.data(), dc.size() * 16);
-        deep_combine_coeffs(stream_, d_tcoef, n, d_ccoef, n, log_n, d_dc, d_pq);
-        lde_columns(tables_, stream_, d_pq, n, d_pqlde, L, d_tmp, 2, log_n, cs);
-        EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[3], 0));
         DeepScalars ds;
         put(ds.z, z), put(ds.zg, zg), put(ds.s1, s1), put(ds.s2, s2);
-        deep_pointwise(stream_, tables_.root_fwd, d_pqlde, log_L, d_invden, ds, sharded ? d_pack : d_deep, sh);
-        if (sharded) share_rows(1, d_deep);
+        if (sharded) {
+            // the pointwise formula on the rows this rank owns: no communication
+            EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[3], 0));
+            deep_from_rows(stream_, tables_.root_fwd, d_tlde, L, d_clde, L, log_L, d_dc, d_invden, ds, d_deep_local, sh);
+        } else {
+            deep_combine_coeffs(stream_, d_tcoef, n, d_ccoef, n, log_n, d_dc, d_pq);
+            lde_columns(tables_, stream_, d_pq, n, d_pqlde, L, d_tmp, 2, log_n, cs);
+            EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[3], 0));
+            deep_pointwise(stream_, tables_.root_fwd, d_pqlde, log_L, d_invden, ds, d_deep, sh);
+        }
     }
     mark();
 
     // ---- (5) FRI ----
     struct Layer {
-        uint4* evals;
-        uint4* nodes;
-        uint64_t size;
+        uint4* evals;       // whole layer in natural order, or (packed) the positions p = me mod G in ascending order
+        bool packed;
+        uint64_t size;      // of the whole layer
+        ShardTree tree;
     };
     std::vector<Layer> layers;
+    layers.reserve(nlayers);
     std::vector<Fp> remainder;
     {
-        uint4* cur = d_deep;
+        uint4* cur = d_deep_local;
+        bool cur_packed = sharded;
         uint64_t s = L;
+        // the positions every rank holds, put back into natural order on every rank (the tail of FRI is replicated)
+        auto gather_natural = [&](uint4* packed, uint64_t size) {
+            uint4* natural = alloc(size);
+            comm_.all_gather(packed, d_allg, (size >> glog) * 16, stream_);
+            count_launch();
+            unpack_rows(stream_, d_allg, size >> glog, glog, 1, natural);
+            return natural;
+        };
         FriFoldConsts fc{};
         const Fp zinv = inverse(root_of_unity(3));
         Fp zp(1);
@@ -579,20 +726,32 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
         put(fc.inv8, inverse(Fp::from_u64(8)));
         for (size_t k = 0; k < nlayers; k++) {
             const uint64_t m = s / 8;
-            uint4* nodes = alloc(4 * m);
-            merkle_hash_rows(stream_, cur, m, 8, m, nodes);
-            merkle_build(stream_, nodes, m);
-            Hash32 root = root_of(nodes);
+            const bool split = cur_packed && m >= shard_fri_min_rows && m >= (uint64_t)G * G;
+            if (cur_packed && !split) cur = gather_natural(cur, s), cur_packed = false;
+            layers.push_back(Layer{cur, split, s, ShardTree{}});
+            Layer& layer = layers.back();
+            Hash32 root;
+            if (split) {
+                // a row is 8 positions at stride m, all of them = i mod G: in packed order again 8 values at stride m / G
+                hash_rows_sharded(stream_, cur, m >> glog, 8, m >> glog, RowShard(), d_pack);
+                root = commit(nullptr, 8, m, nullptr, layer.tree);
+            } else {
+                uint4* nodes = alloc(4 * m);
+                const bool was = sharded;
+                sharded = false;  // whole-layer tree on every rank
+                root = commit(cur, 8, m, nodes, layer.tree);
+                sharded = was;
+            }
             commitments.insert(commitments.end(), root.begin(), root.end());
             coin.reseed(root);
             last_.fri_roots.push_back(root);
             const Fp alpha = coin.draw();
             put(fc.alpha_oinv, alpha * o_inv);
-            uint4* next = alloc(m);
-            fri_fold(stream_, tables_.root_inv, cur, ilog2_u64(s), fc, next);
-            layers.push_back(Layer{cur, nodes, s});
+            uint4* next = alloc(split ? (m >> glog) : m);
+            fri_fold(stream_, tables_.root_inv, cur, ilog2_u64(s), fc, next, split ? sh : RowShard());
             cur = next, s = m;
         }
+        if (cur_packed) cur = gather_natural(cur, s), cur_packed = false;
         // remainder: interpolate the last layer over the coset; only the first s/8 coefficients may be non-zero
         uint4* d_rem = alloc(s);
         {
@@ -641,77 +800,100 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     w.bytes(commitments.data(), commitments.size());
 
     // All openings (trace rows, constraint rows, one per FRI layer) are planned on the host first, fetched with ONE
-    // index upload, a burst of gather kernels and ONE read-back, and serialized afterwards.
+    // index upload, a burst of gather kernels and ONE read-back, and serialized afterwards.  Multi-GPU: every rank
+    // plans the same openings, gathers the rows and subtree nodes it owns (any index elsewhere), the gather buffers
+    // are all-gathered and each item is taken from its owner's copy; the top log2(G) tree levels live on the host.
     uint64_t* d_idx = reinterpret_cast<uint64_t*>(alloc(8192));  // up to 16384 u64 indices
     uint4* d_gather = alloc(32768);
     struct Opening {
         const uint4* table;
         uint64_t pitch;
         uint32_t width;
-        const uint4* nodes;
-        uint64_t num_leaves;
+        const ShardTree* tree;
         std::vector<uint64_t> pos;
-        std::vector<std::vector<uint64_t>> idx_lists;
+        std::vector<uint32_t> row_owner;                   // rank whose gather buffer holds row q
+        std::vector<std::vector<uint64_t>> idx_lists;      // global node indices, serialization order
+        std::vector<int32_t> dig_owner;                    // per digest: owning rank, or -1 = host-side top levels
+        std::vector<uint64_t> dig_top;                     // per digest: index into tree->top when dig_owner < 0
         size_t idx_off, ndig, out_off;  // offsets into the index array / the gather buffer (16-byte units)
     };
     std::vector<Opening> ops;
+    ops.reserve(2 + nlayers);
     std::vector<uint64_t> flat;
     size_t out_units = 0;
-    auto plan_opening = [&](const uint4* table, uint64_t pitch, uint32_t width, const uint4* nodes, uint64_t num_leaves,
+    // rows_mode 0: whole table on this rank; 1: rows owned by p mod G at index p (LDE tables keep the global row index);
+    // 2: rows owned by p mod G at index p / G (packed FRI layer)
+    auto plan_opening = [&](const uint4* table, uint64_t pitch, uint32_t width, const ShardTree* tree, int rows_mode,
                             const std::vector<uint64_t>& pos) {
-        Opening o{table, pitch, width, nodes, num_leaves, pos, batch_proof_node_indices(num_leaves, pos), flat.size(), 0, out_units};
-        flat.insert(flat.end(), pos.begin(), pos.end());
-        for (auto& v : o.idx_lists) flat.insert(flat.end(), v.begin(), v.end());
-        o.ndig = flat.size() - o.idx_off - pos.size();
-        out_units += pos.size() * width + 2 * o.ndig;
-        ops.push_back(std::move(o));
+        Opening op{table, pitch, width, tree, pos, {}, batch_proof_node_indices(tree->leaves, pos), {}, {}, flat.size(), 0, out_units};
+        for (uint64_t p : pos) {
+            const uint32_t owner = rows_mode == 0 ? me : (uint32_t)(p & (G - 1));
+            op.row_owner.push_back(owner);
+            flat.push_back(owner != me ? 0 : rows_mode == 2 ? p >> glog : p);
+        }
+        for (auto& v : op.idx_lists)
+            for (uint64_t k : v) {
+                if (!tree->split) {
+                    op.dig_owner.push_back((int32_t)me), op.dig_top.push_back(0), flat.push_back(k);
+                } else if (k < 2ull * G) {
+                    op.dig_owner.push_back(-1), op.dig_top.push_back(k), flat.push_back(1);
+                } else {
+                    const unsigned d = ilog2_floor(k) - glog;  // depth below the subtree roots
+                    const uint32_t owner = (uint32_t)((k >> d) - G);
+                    op.dig_owner.push_back((int32_t)owner), op.dig_top.push_back(0);
+                    flat.push_back(owner == me ? ((1ull << d) | (k & ((1ull << d) - 1))) : 1);
+                }
+            }
+        op.ndig = op.dig_owner.size();
+        out_units += pos.size() * width + 2 * op.ndig;
+        ops.push_back(std::move(op));
     };
-    plan_opening(d_tlde, L, kWidth, d_tnodes, L, positions);
-    plan_opening(d_clde, L, kCompCols, d_cnodes, L, positions);
-    const size_t lde_units = out_units;  // the part that holds rows of the (possibly sharded) LDE tables
+    plan_opening(d_tlde, L, kWidth, &trace_tree, sharded ? 1 : 0, positions);
+    plan_opening(d_clde, L, kCompCols, &comp_tree, sharded ? 1 : 0, positions);
     {
         std::vector<uint64_t> pos = positions;
         for (auto& layer : layers) {
             pos = fold_positions(pos, layer.size, 8);
-            plan_opening(layer.evals, layer.size / 8, 8, layer.nodes, layer.size / 8, pos);
+            const uint64_t m = layer.size / 8;
+            plan_opening(layer.evals, layer.packed ? m >> glog : m, 8, &layer.tree, layer.packed ? 2 : 0, pos);
         }
     }
-    if (flat.size() > 16384 || out_units > 32768 || out_units * 16 * (sharded ? comm_.world() : 1) > pinned_bytes_)
+    const bool exchange = sharded && G > 1;
+    if (flat.size() > 16384 || out_units > 32768 || out_units * 16 * (exchange ? G : 1) > pinned_bytes_)
         throw ProveFailure{EZK_ERR_INTERNAL, "query staging too small"};
     h2d(d_idx, flat.data(), flat.size() * 8);
-    for (auto& o : ops) {
-        const uint32_t nq = (uint32_t)o.pos.size();
-        gather_rows(stream_, o.table, o.pitch, o.width, d_idx + o.idx_off, nq, d_gather + o.out_off);
-        if (o.ndig)
-            gather_digests(stream_, o.nodes, d_idx + o.idx_off + nq, (uint32_t)o.ndig, d_gather + o.out_off + (size_t)nq * o.width);
+    for (auto& op : ops) {
+        const uint32_t nq = (uint32_t)op.pos.size();
+        gather_rows(stream_, op.table, op.pitch, op.width, d_idx + op.idx_off, nq, d_gather + op.out_off);
+        if (op.ndig)
+            gather_digests(stream_, op.tree->nodes, d_idx + op.idx_off + nq, (uint32_t)op.ndig, d_gather + op.out_off + (size_t)nq * op.width);
     }
-    std::vector<uint8_t> fetched(out_units * 16);
-    d2h(fetched.data(), d_gather, fetched.size());
-    if (sharded) {
-        // the LDE tables hold only this rank's rows: take every opened row from the all-gathered copy of its owner
-        // (the Merkle nodes are replicated on every rank)
-        comm_.all_gather(d_gather, d_allg, lde_units * 16, stream_);
+    std::vector<uint8_t> fetched(out_units * 16), all;
+    if (exchange) {
+        comm_.all_gather(d_gather, d_allg, out_units * 16, stream_);
         count_launch();
-        std::vector<uint8_t> all(lde_units * 16 * comm_.world());
+        all.resize(out_units * 16 * G);
         d2h(all.data(), d_allg, all.size());
-        for (size_t k = 0; k < 2; k++)
-            for (size_t q = 0; q < ops[k].pos.size(); q++) {
-                const size_t off = (ops[k].out_off + q * ops[k].width) * 16;
-                memcpy(fetched.data() + off, all.data() + sh.owner(ops[k].pos[q]) * lde_units * 16 + off, (size_t)ops[k].width * 16);
-            }
+    } else {
+        d2h(fetched.data(), d_gather, fetched.size());
     }
-    auto write_opening = [&](const Opening& o) {
-        const size_t vbytes = o.pos.size() * o.width * 16;
-        const uint8_t* base = fetched.data() + o.out_off * 16;
-        w.u32((uint32_t)vbytes);
-        w.bytes(base, vbytes);
+    auto item = [&](uint32_t owner, size_t unit) -> const uint8_t* {  // `unit` = offset in 16-byte words in a gather buffer
+        return exchange ? all.data() + ((size_t)owner * out_units + unit) * 16 : fetched.data() + unit * 16;
+    };
+    auto write_opening = [&](const Opening& op) {
+        const size_t nq = op.pos.size();
+        w.u32((uint32_t)(nq * op.width * 16));
+        for (size_t q = 0; q < nq; q++) w.bytes(item(op.row_owner[q], op.out_off + q * op.width), (size_t)op.width * 16);
         std::vector<uint8_t> paths;
-        paths.push_back((uint8_t)o.idx_lists.size());
-        const uint8_t* dg = base + vbytes;
-        for (auto& v : o.idx_lists) {
+        paths.push_back((uint8_t)op.idx_lists.size());
+        size_t d = 0;
+        for (auto& v : op.idx_lists) {
             paths.push_back((uint8_t)v.size());
-            paths.insert(paths.end(), dg, dg + v.size() * 32);
-            dg += v.size() * 32;
+            for (size_t k = 0; k < v.size(); k++, d++) {
+                const uint8_t* src = op.dig_owner[d] < 0 ? op.tree->top[op.dig_top[d]].data()
+                                                         : item((uint32_t)op.dig_owner[d], op.out_off + nq * op.width + 2 * d);
+                paths.insert(paths.end(), src, src + 32);
+            }
         }
         w.u32((uint32_t)paths.size());
         w.bytes(paths.data(), paths.size());
@@ -719,7 +901,7 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
     write_opening(ops[0]);
     write_opening(ops[1]);
     // OodFrame
-    w.u16((uint16_t)(1 + ood_trace.size() * 16));
+    w.u16((uint16_t)(1 + ood_wire.size() * 16));
     w.u8(2);
     for (Fp v : ood_wire) w.element(v);
     w.u16(1), w.u8(0);

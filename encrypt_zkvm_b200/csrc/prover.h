@@ -36,6 +36,8 @@ public:
     // same trace, public inputs and options; each rank extends / evaluates / hashes the LDE cosets it owns, the
     // per-row products are all-gathered over NCCL, and every rank returns the same proof bytes.
     void join(int rank, int world, const uint8_t unique_id[128]);
+    // the same with an in-process group (several provers of one process, one host thread each): tests on one GPU
+    void join_local(int rank, LocalGroup* group);
     int world() const { return comm_.world(); }
 
     // winterfell::verify for this AIR (vm/src/lib.rs:91-98); throws ProveFailure{EZK_ERR_VERIFICATION} on rejection
@@ -59,6 +61,8 @@ public:
     void bench_fri(uint64_t n, int iters, float* fri_ms);
 
 private:
+    std::vector<uint8_t> prove_impl(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
+                                    const PublicInputs& pub, const ProofOptions& opt);
     struct Arena {
         uint4* base = nullptr;
         size_t capacity = 0, used = 0;  // in 16-byte units
@@ -74,6 +78,7 @@ private:
     cudaEvent_t copy_ev_[16];
     cudaStream_t aux_stream_ = nullptr;   // small independent kernels overlapped with latency-bound phases
     cudaEvent_t aux_ev_[4];
+    cudaEvent_t share_ev_[64];            // multi-GPU: interpolation of a column round done / its all-gather done
     NttTables tables_;
     Comm comm_;
     Arena arena_;

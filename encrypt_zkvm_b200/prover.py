@@ -215,6 +215,13 @@ class ExecutionProver:
     def leave_group(self) -> None:
         check(lib.ezk_prover_join(self._handle, 0, 1, bytes(128)))
 
+    def join_local(self, group: "LocalGroup", rank: int) -> None:
+        """Member `rank` of an in-process group (see LocalGroup); prove() must then run in one host thread per member."""
+        check(lib.ezk_prover_join_local(self._handle, group._handle, rank))
+
+    def leave_local(self) -> None:
+        check(lib.ezk_prover_join_local(self._handle, None, 0))
+
     # -- timing -----------------------------------------------------------------------------------------
     def timer_start(self) -> None:
         check(lib.ezk_prover_timer_start(self._handle))
@@ -298,6 +305,69 @@ class ExecutionProver:
         a = C.c_float()
         check(lib.ezk_bench_fri(self._handle, n, iters, C.byref(a)))
         return a.value
+
+
+class LocalGroup:
+    """Several provers of ONE process as the ranks of a sharded proof (host-synchronised device copies instead of
+    NCCL; include/ezkvm_prover.h).  `prove_sharded` runs one proof with `world` members on the given devices - all on
+    cuda:0 by default, which is how the sharded pipeline is tested on a one-GPU box."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self._handle = C.c_void_p()
+        check(lib.ezk_local_group_create(world, C.byref(self._handle)))
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None) and self._handle.value:
+            lib.ezk_local_group_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def prove_sharded_in_process(world: int, options: ProofOptions, program_hash, stack_outputs, server_key: ServerKey, trace,
+                             devices: Optional[Sequence[int]] = None, device_ptr: Optional[int] = None, own_columns_only=False):
+    """One proof by `world` provers of this process (threads), returns the list of the members' proof bytes.
+    own_columns_only: member r is handed a trace in which every column it does not own is poisoned."""
+    import threading
+    a = _as_trace_array(trace)
+    devices = list(devices) if devices is not None else [0] * world
+    group = LocalGroup(world)
+    provers = [ExecutionProver(options, program_hash, stack_outputs, server_key, device=devices[r]) for r in range(world)]
+    out, err = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            provers[r].join_local(group, r)
+            if device_ptr is not None:
+                out[r] = provers[r].prove_device(device_ptr, a.shape[1]).to_bytes()
+            else:
+                t = a
+                if own_columns_only:
+                    t = a.copy()
+                    for c in range(TRACE_WIDTH):
+                        if c % world != r:
+                            t[c] = 0xFFFFFFFFFFFFFFFF  # not even canonical: a rank that read it would fail
+                out[r] = provers[r].prove(t).to_bytes()
+        except Exception as e:  # noqa: BLE001 - reported to the caller below
+            err[r] = e
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for p in provers:
+        p.close()
+    group.close()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
 
 
 def verify(proof, pub_inputs: PublicInputs, min_conjectured_security: int = 95, device: int = 0) -> None:

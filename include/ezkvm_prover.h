@@ -124,12 +124,29 @@ int ezk_prover_verify(ezk_prover* p, const uint8_t* proof, size_t proof_len, con
 /* ---- one proof sharded over the GPUs of a box (no reference counterpart: the reference is one thread) ----
  * One process per GPU.  Rank 0 calls ezk_comm_unique_id and hands the 128 bytes to the other ranks (any
  * transport; the Python binding uses torch.distributed); every rank then calls ezk_prover_join on its own
- * prover (a collective: it builds the NCCL communicator).  From then on ezk_prover_prove must be called by ALL
- * ranks with the same trace / public inputs / options: rank r extends, evaluates and hashes the LDE cosets
- * {c : c mod world = r}, the per-row products travel over NVLink (ncclAllGather), and every rank returns the
- * same proof bytes, identical to the single-GPU proof.  world in {1, 2, 4, 8}; world = 1 leaves the group. */
+ * prover (a collective: it builds the NCCL communicator).  From then on ezk_prover_prove / _prove_device must be
+ * called by ALL ranks with the same trace length / public inputs / options.  Rank r of `world`
+ *   - reads only the trace columns c with c mod world = r (the other column pointers / device columns are never
+ *     touched: a caller may hand every rank only its own columns), interpolates them and all-gathers the coefficients;
+ *   - extends, hashes and evaluates the LDE rows i with i mod world = r (whole cosets);
+ *   - holds the Merkle subtree over the leaves [r L / world, (r + 1) L / world) of every commitment: leaf digests move
+ *     with one all-to-all, only the `world` subtree roots are gathered;
+ *   - interpolates the constraint evaluations on its cosets; the composition columns come from an all-gather of those
+ *     coefficient arrays and an 8-point inverse DFT across the cosets;
+ *   - evaluates the out-of-domain frame for its columns, the DEEP composition and the large FRI layers for its rows.
+ * Every rank returns the same proof bytes, identical to the single-GPU proof.  world in {1, 2, 4, 8}; world = 1
+ * leaves the group.  A proof that fails input validation fails on every rank; any other failure on one rank of an
+ * NCCL group leaves the others waiting in a collective (abort the processes). */
 int ezk_comm_unique_id(uint8_t out[128]);
 int ezk_prover_join(ezk_prover* p, int rank, int world, const uint8_t unique_id[128]);
+
+/* The same sharded proof between several provers of ONE process (one host thread per prover, any mix of devices,
+ * also all on one GPU): the exchanges are host-synchronised device copies instead of NCCL.  Not a performance path:
+ * it runs the whole sharded pipeline on a one-GPU box (tests).  group = NULL leaves the group. */
+typedef struct ezk_group ezk_group;
+int ezk_local_group_create(int world, ezk_group** out);
+void ezk_local_group_destroy(ezk_group* g);
+int ezk_prover_join_local(ezk_prover* p, ezk_group* g, int rank);
 
 /* Device-time of the stages of the last proof, milliseconds (CUDA events on the prover's stream). */
 enum ezk_stage {
