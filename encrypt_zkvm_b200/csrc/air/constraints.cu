@@ -85,10 +85,12 @@ struct SumSink {
 template <class AR>
 __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, const uint4* __restrict__ lde, uint64_t pitch,
                                                uint32_t log_L, const ConstraintParams* __restrict__ p,
-                                               const uint4* __restrict__ inv_den, uint64_t packed, uint64_t i, fe& result) {
-    const uint64_t L = 1ull << log_L;
+                                               const uint4* __restrict__ inv_den, RowShard sh, uint64_t packed, uint64_t i,
+                                               fe& result) {
+    const uint64_t L_local = (1ull << log_L) >> sh.world_log;
     AR ar;
-    LdeFrame f{lde, pitch, i, (i + 8) & (L - 1)};
+    // the table holds this rank's rows in packed order: row i + 8 sits 8 / world entries after row i
+    LdeFrame f{lde, pitch, packed, (packed + sh.frame_step()) & (L_local - 1)};
     fe periodic[9];
     {
         const uint64_t(*row)[2] = &p->ptable[(i & 127) * 9];
@@ -122,9 +124,9 @@ __device__ __forceinline__ bool constraint_row(const uint4* __restrict__ roots, 
 
 __device__ __noinline__ fe constraint_row_exact(const uint4* __restrict__ roots, const uint4* __restrict__ lde, uint64_t pitch,
                                                 uint32_t log_L, const ConstraintParams* __restrict__ p,
-                                                const uint4* __restrict__ inv_den, uint64_t t, uint64_t i) {
+                                                const uint4* __restrict__ inv_den, RowShard sh, uint64_t t, uint64_t i) {
     fe r;
-    constraint_row<Arith<false>>(roots, lde, pitch, log_L, p, inv_den, t, i, r);
+    constraint_row<Arith<false>>(roots, lde, pitch, log_L, p, inv_den, sh, t, i, r);
     return r;
 }
 
@@ -138,8 +140,8 @@ __global__ void __launch_bounds__(THREADS, MINB) constraint_kernel(const uint4* 
     if (t >= ((1ull << log_L) >> sh.world_log)) return;
     const uint64_t i = sh.global_row(t);
     fe r;
-    if (constraint_row<AR>(roots, lde, pitch, log_L, p, inv_den, t, i, r))
-        r = constraint_row_exact(roots, lde, pitch, log_L, p, inv_den, t, i);
+    if (constraint_row<AR>(roots, lde, pitch, log_L, p, inv_den, sh, t, i, r))
+        r = constraint_row_exact(roots, lde, pitch, log_L, p, inv_den, sh, t, i);
     // packed order (t = rows of this rank in ascending order) or one contiguous array of n values per owned coset
     // (what the per-coset interpolation of the sharded composition step reads)
     const uint32_t cn_log = 3 - sh.world_log;

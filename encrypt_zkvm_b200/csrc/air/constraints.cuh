@@ -33,7 +33,7 @@ int domain_pair_inverse(cudaStream_t s, const uint4* root_fwd, const uint4* root
                         const uint64_t b[2], uint4* out, RowShard sh = RowShard());
 
 // combined[i] = T_i / z_t(x_i) + B0_i / (x_i - 1) + B1_i / (x_i - g^(n-2))   
-// lde: column-major 28 x L; inv_den[i] = 1/((x_i - 1)(x_i - g^(n-2)))
+// lde: column-major 28 x (L / world) rows in packed order; inv_den[t] = 1/((x_i - 1)(x_i - g^(n-2))), i = global_row(t)
 // coset_major: combined[k * n + j] for the k-th coset this rank owns (LDE row 8 j + coset) instead of packed row order
 int evaluate_constraints(cudaStream_t s, const uint4* root_fwd, const uint4* lde, uint64_t pitch, uint32_t log_L,
                          const ConstraintParams* params, const uint4* inv_den, uint4* combined, RowShard sh = RowShard(),

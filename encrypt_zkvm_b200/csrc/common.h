@@ -59,10 +59,11 @@ struct LaunchScope {
     int slot;
 };
 
-// Multi-GPU row ownership: rank r of 2^world_log ranks owns the LDE rows i with (i mod 8) mod world = r,
-// i.e. whole cosets, so the (row i, row i + 8) frames of the constraint evaluation and the 8 points of a FRI
-// layer-0 row stay on one GPU.  Row kernels run over the packed index t < L / world and address tables with
-// the global row i = global_row(t); with one GPU global_row is the identity.
+// Multi-GPU row ownership: rank r of 2^world_log ranks owns the LDE rows i with i mod world = r, i.e. whole
+// cosets, so the (row i, row i + 8) frames of the constraint evaluation and the 8 points of a FRI layer-0 row stay on
+// one GPU.  A rank keeps its rows in ascending order ("packed": row i = world * t + r at index t < L / world), tables
+// included; row kernels run over t, take the domain point from global_row(t), and find the row 8 steps ahead at
+// t + 8 / world.  With one GPU global_row is the identity.
 struct RowShard {
     uint32_t rank = 0, world_log = 0;
     __host__ __device__ uint64_t global_row(uint64_t t) const {
@@ -70,6 +71,7 @@ struct RowShard {
         return ((t >> cn_log) << 3) + rank + ((t & ((1u << cn_log) - 1)) << world_log);
     }
     __host__ __device__ uint32_t owner(uint64_t i) const { return (uint32_t)(i & ((1u << world_log) - 1)); }
+    __host__ __device__ uint32_t frame_step() const { return 8u >> world_log; }  // packed distance of LDE rows i and i + 8
 };
 
 inline unsigned ilog2_u64(uint64_t n) {

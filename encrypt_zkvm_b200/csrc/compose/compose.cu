@@ -133,7 +133,27 @@ __global__ void __launch_bounds__(256) deep_pointwise_kernel(const uint4* __rest
 }
 
 // DEEP composition straight from the LDE tables (multi-GPU: everything a rank needs is in the rows it owns):
-// P_i = sum_c dc[c] T_c(x_i), Q_i = sum_j dc[28 + j] H_j(x_i), then the same quotient as deep_pointwise_kernel
+// P_i = sum_c dc[c] T_c(x_i), Q_i = sum_j dc[28 + j] H_j(x_i), then the same quotient as deep_pointwise_kernel.
+// Flagged arithmetic with an exact redo of the row, as in the constraint kernel.
+template <class AR>
+__device__ __forceinline__ bool deep_row(const uint4* __restrict__ roots, const uint4* __restrict__ tlde, uint64_t tpitch,
+                                         const uint4* __restrict__ clde, uint64_t cpitch, uint32_t log_L,
+                                         const uint4* __restrict__ dc, fe inv, const DeepScalars& sc, uint64_t t, uint64_t i,
+                                         fe& out) {
+    AR ar;
+    fe P = fe_zero(), Q = fe_zero();
+#pragma unroll 7
+    for (int c = 0; c < 28; c++) P = ar.add(P, ar.mul(fe_ldg(dc + c), fe_ldg(tlde + (uint64_t)c * tpitch + t)));
+#pragma unroll
+    for (int j = 0; j < 7; j++) Q = ar.add(Q, ar.mul(fe_ldg(dc + 28 + j), fe_ldg(clde + (uint64_t)j * cpitch + t)));
+    const fe w = fe_root_pow(roots, log_L, i);
+    const fe x = ar.add(ar.add(w, w), w);
+    const fe t1 = ar.sub(ar.add(P, Q), fe_make(sc.s1[0], sc.s1[1]));
+    const fe t2 = ar.sub(P, fe_make(sc.s2[0], sc.s2[1]));
+    const fe num = ar.add(ar.mul(t1, ar.sub(x, fe_make(sc.zg[0], sc.zg[1]))), ar.mul(t2, ar.sub(x, fe_make(sc.z[0], sc.z[1]))));
+    out = ar.mul(num, inv);
+    return ar.tainted();
+}
 __global__ void __launch_bounds__(256) deep_rows_kernel(const uint4* __restrict__ roots, const uint4* __restrict__ tlde,
                                                        uint64_t tpitch, const uint4* __restrict__ clde, uint64_t cpitch,
                                                        uint32_t log_L, const uint4* __restrict__ dc,
@@ -143,17 +163,11 @@ __global__ void __launch_bounds__(256) deep_rows_kernel(const uint4* __restrict_
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (L >> sh.world_log)) return;
     const uint64_t i = sh.global_row(t);
-    fe P = fe_zero(), Q = fe_zero();
-#pragma unroll 4
-    for (int c = 0; c < 28; c++) P = fe_add(P, fe_mul(fe_ldg(dc + c), fe_ldg(tlde + (uint64_t)c * tpitch + i)));
-#pragma unroll
-    for (int j = 0; j < 7; j++) Q = fe_add(Q, fe_mul(fe_ldg(dc + 28 + j), fe_ldg(clde + (uint64_t)j * cpitch + i)));
-    fe w = fe_root_pow(roots, log_L, i);
-    fe x = fe_add(fe_add(w, w), w);
-    fe t1 = fe_sub(fe_add(P, Q), fe_make(sc.s1[0], sc.s1[1]));
-    fe t2 = fe_sub(P, fe_make(sc.s2[0], sc.s2[1]));
-    fe num = fe_add(fe_mul(t1, fe_sub(x, fe_make(sc.zg[0], sc.zg[1]))), fe_mul(t2, fe_sub(x, fe_make(sc.z[0], sc.z[1]))));
-    fe_store(deep + t, fe_mul(num, fe_ldg(inv_den + t)));
+    const fe inv = fe_ldg(inv_den + t);
+    fe r;
+    if (deep_row<Arith<true>>(roots, tlde, tpitch, clde, cpitch, log_L, dc, inv, sc, t, i, r))
+        deep_row<Arith<false>>(roots, tlde, tpitch, clde, cpitch, log_L, dc, inv, sc, t, i, r);
+    fe_store(deep + t, r);
 }
 
 __global__ void all_zero_kernel(const uint4* __restrict__ v, uint64_t count, uint32_t* flag) {

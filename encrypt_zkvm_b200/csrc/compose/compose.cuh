@@ -35,7 +35,7 @@ int deep_pointwise(cudaStream_t s, const uint4* root_fwd, const uint4* pq_lde, u
 
 // The same DEEP evaluations from the LDE tables instead of the coefficient tables (the pointwise
 // formula on LDE rows gives identical values): deep[t] for the packed rows t of this rank, reading only rows it owns.
-// Used by the multi-GPU path, where it needs no communication.  tlde: 28 columns, clde: 7 columns (global row index).
+// Used by the multi-GPU path, where it needs no communication.  tlde: 28 columns, clde: 7 columns (packed row order).
 int deep_from_rows(cudaStream_t s, const uint4* root_fwd, const uint4* tlde, uint64_t tpitch, const uint4* clde, uint64_t cpitch,
                    uint32_t log_L, const uint4* deep_coeffs /* 28 + 7 */, const uint4* inv_den, DeepScalars sc, uint4* deep,
                    RowShard sh);

@@ -16,16 +16,14 @@ constexpr int kThreads = 256;
 // the block loop is unrolled and the block lengths and flags are immediates; WIDTH = 0: any width.
 template <int WIDTH>
 __global__ void __launch_bounds__(kThreads) hash_rows_kernel(const uint4* __restrict__ table, uint64_t pitch,
-                                                            uint32_t width_rt, uint64_t rows, RowShard sh,
-                                                            uint4* __restrict__ leaves) {
+                                                            uint32_t width_rt, uint64_t rows, uint4* __restrict__ leaves) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows) return;
-    const uint64_t i = sh.global_row(t);
     const uint32_t width = WIDTH > 0 ? (uint32_t)WIDTH : width_rt;
     uint32_t cv[8];
     b3_init(cv);
     const uint32_t nblocks = (width + 3) / 4;
-    const uint4* cell = table + i;
+    const uint4* cell = table + t;  // multi-GPU: tables hold this rank's rows in packed order
 #pragma unroll
     for (uint32_t b = 0; b < (WIDTH > 0 ? (uint32_t)(WIDTH + 3) / 4 : nblocks); b++) {
         uint32_t m[16];
@@ -103,19 +101,19 @@ int merkle_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_
     return hash_rows_sharded(s, table, pitch, width, rows, RowShard(), nodes + 2 * rows);
 }
 
-int hash_rows_sharded(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard sh,
+int hash_rows_sharded(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard,
                       uint4* digests) {
     unsigned blocks = (unsigned)((local_rows + kThreads - 1) / kThreads);
     {
         LaunchScope ls(s, K_HASH_ROWS, local_rows * ((uint64_t)width * 16 + 32));
         if (width == 28)
-            hash_rows_kernel<28><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
+            hash_rows_kernel<28><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, digests);
         else if (width == 7)
-            hash_rows_kernel<7><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
+            hash_rows_kernel<7><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, digests);
         else if (width == 8)
-            hash_rows_kernel<8><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
+            hash_rows_kernel<8><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, digests);
         else
-            hash_rows_kernel<0><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, sh, digests);
+            hash_rows_kernel<0><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, digests);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;

@@ -13,7 +13,8 @@ namespace ezk {
 
 // leaf i = blake3(row i as little-endian bytes), row i = (table[c * pitch + i])_{c < width}
 int merkle_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t rows, uint4* nodes);
-// multi-GPU: digests[t] = blake3(row global_row(t)) for the local_rows rows this rank owns (packed order)
+// multi-GPU: digests[t] = blake3(row t of the table) for the local_rows rows this rank holds (packed order: table row t
+// is LDE row global_row(t))
 int hash_rows_sharded(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard sh,
                       uint4* digests);
 // dst[global_row_q(t)] = gathered[q][t] for the 2^world_log all-gathered blocks of per_rank items (units x 16 bytes each)

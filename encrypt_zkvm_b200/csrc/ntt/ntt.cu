@@ -477,8 +477,9 @@ struct FinalPass {
             out.index = ((uint64_t)jg << log_H) + out_base + lane;
             out.step = 1ull << (log_s - 3 + log_H);
         } else {
-            out.index = ((((uint64_t)jg << log_H) + out_base) << 3) + a->cs_base + a->cs_step * (coset0 + lane);
-            out.step = 1ull << (log_s - 3 + log_H + 3);
+            // packed row order: the rows of the cosets this prover computes, ascending (all 8 cosets: the natural order)
+            out.index = ((((uint64_t)jg << log_H) + out_base) << a->cs_log) + coset0 + lane;
+            out.step = 1ull << (log_s - 3 + log_H + a->cs_log);
         }
         out.ptr = dst + out.index;
         return out;

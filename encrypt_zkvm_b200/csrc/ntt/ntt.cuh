@@ -59,9 +59,11 @@ struct CosetSet {
     uint32_t count_log = 3, base = 0, step = 1;
 };
 
-// Coset low-degree extension with blowup 8: coeff[c][m] must already be scaled by o^m; writes
-// lde[c][8j + k] = sum_m coeff[c][m] * (w_L^k)^m * w_n^(mj)   (natural order over the LDE domain o*<w_L>).
-// Only the rows of the cosets in `cs` are written (the others are left untouched).
+// Coset low-degree extension with blowup 8: coeff[c][m] must already be scaled by o^m.  For the k-th coset of `cs`
+// (coset number q_k = base + step * k) and j < n:
+//     lde[c][(j << count_log) + k] = sum_m coeff[c][m] * (w_L^(q_k))^m * w_n^(mj)  =  column c at LDE row 8 j + q_k,
+// i.e. the rows of the chosen cosets in ascending order ("packed" row order; with all 8 cosets it is the natural order
+// over the LDE domain o*<w_L>).  lde_pitch >= n << count_log.
 // tmp must hold ncols * (number of cosets) * n elements when n > 2^max_tile_log (unused otherwise).
 int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t coeff_pitch, uint4* lde,
                 uint64_t lde_pitch, uint4* tmp, uint32_t ncols, uint32_t log_n, CosetSet cs = CosetSet());

@@ -117,7 +117,13 @@ GpuProver::GpuProver(int device) : device_(device) {
     for (auto& e : ev_) EZK_CUDA(cudaEventCreate(&e));
     for (auto& e : timer_ev_) EZK_CUDA(cudaEventCreate(&e));
     EZK_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-    EZK_CUDA(cudaStreamCreateWithFlags(&aux_stream_, cudaStreamNonBlocking));
+    {
+        // the auxiliary stream carries the NCCL exchanges of the sharded proof and small kernels that must slip in
+        // beside long transforms: highest priority, so its CTAs are scheduled as soon as the compute stream retires some
+        int lo = 0, hi = 0;
+        EZK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        EZK_CUDA(cudaStreamCreateWithPriority(&aux_stream_, cudaStreamNonBlocking, hi));
+    }
     for (auto& e : aux_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : copy_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : share_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -313,13 +319,13 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     reset_arena();
     uint4* d_trace_in = host_columns ? alloc(kWidth * n) : nullptr;
     uint4* d_tcoef = alloc((size_t)(sharded ? rounds * G : kWidth) * n);
-    uint4* d_tlde = alloc(kWidth * L);
+    uint4* d_tlde = alloc(kWidth * L_local);  // multi-GPU: this rank's rows only, packed order
     uint4* d_tmp = alloc(kWidth * L);
     uint4* d_tnodes = sharded ? nullptr : alloc(4 * L);
     uint4* d_invden = alloc(L);
     uint4* d_combined = alloc(L);
     uint4* d_ccoef = alloc(L);
-    uint4* d_clde = alloc(kCompCols * L);
+    uint4* d_clde = alloc(kCompCols * L_local);
     uint4* d_cnodes = sharded ? nullptr : alloc(4 * L);
     uint4* d_pq = alloc(2 * n);
     uint4* d_pqlde = sharded ? nullptr : alloc(2 * L);
@@ -345,6 +351,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     if (!sharded) last_.tlde = d_tlde, last_.clde = d_clde, last_.combined_copy = d_combined, last_.deep = d_deep;
 
     int evi = 0;
+    bool mark_pending = false;
     auto mark = [&]() { EZK_CUDA(cudaEventRecord(ev_[evi++], stream_)); };
     auto d2h = [&](void* dst, const void* src, size_t bytes) {
         if (bytes > pinned_bytes_) throw ProveFailure{EZK_ERR_INTERNAL, "staging buffer too small"};
@@ -370,7 +377,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
             return root;
         }
         const uint64_t ll = leaves >> glog;  // leaves of this rank's subtree
-        if (table) hash_rows_sharded(stream_, table, leaves, width, ll, sh, d_pack);
+        if (table) hash_rows_sharded(stream_, table, ll, width, ll, sh, d_pack);
         // rank r's packed digests are those of rows r, r + G, ...: chunk q of them lies in rank q's leaf range
         tree.split = true, tree.leaves_local = ll, tree.nodes = alloc(4 * ll);
         comm_.all_to_all(d_pack, d_recv, (ll >> glog) * 32, stream_);
@@ -401,45 +408,60 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         put(sc.cvec[0], inverse(Fp::from_u64(n)));
         sc.chunk_shift = 63, sc.use_offset = 1;
         if (sharded) {
-            // this rank interpolates the columns c = me, me + G, ... (uploading only those), round j of every rank is
-            // all-gathered in place into columns [jG, jG + G) on the auxiliary stream, and the extension of a round's
-            // columns over this rank's cosets starts as soon as the round has arrived
+            // this rank interpolates the columns c = me, me + G, ... (uploading only those); round j of every rank
+            // (columns [jG, jG + G)) is all-gathered in place on the auxiliary stream, and the extension of a batch of
+            // rounds (about 8 columns per launch) over this rank's cosets starts as soon as the batch has arrived
             EZK_CUDA(cudaEventRecord(copy_ev_[15], stream_));
             EZK_CUDA(cudaStreamWaitEvent(copy_stream_, copy_ev_[15], 0));  // the arena may still be in use
             EZK_CUDA(cudaStreamWaitEvent(aux_stream_, copy_ev_[15], 0));
             const bool staged = host_columns && use_staged_upload(host_columns);
+            const uint4* own_src = device_trace ? device_trace : d_trace_in;
+            const uint32_t rb = std::max(1u, 8u / G);  // rounds per batch: about 8 columns per extension launch
             uint64_t chunk = 0;
-            bool first = true;
-            for (uint32_t j = 0; j < rounds; j++) {
-                const uint32_t c = j * G + me;
-                if (c < kWidth) {
-                    const uint4* src = device_trace ? device_trace + (size_t)c * n : d_trace_in + (size_t)c * n;
+            mark_pending = true;
+            auto extend_batch = [&](uint32_t j0) {
+                const uint32_t j1 = std::min(rounds, j0 + rb);
+                EZK_CUDA(cudaStreamWaitEvent(stream_, share_ev_[2 * (j1 - 1) + 1], 0));
+                const size_t c0 = (size_t)j0 * G;
+                const uint32_t cols = std::min<uint32_t>((j1 - j0) * G, kWidth - (uint32_t)c0);
+                lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L_local, L_local, d_tmp, cols, log_n, cs);
+            };
+            // software pipeline on the compute stream: interpolate(b), extend(b - 1), interpolate(b + 1), ... so that the
+            // all-gather of batch b (auxiliary stream) and the upload of batch b + 1 run under the extension of batch b - 1
+            for (uint32_t j0 = 0; j0 < rounds; j0 += rb) {
+                const uint32_t j1 = std::min(rounds, j0 + rb);
+                uint32_t own = 0;  // own columns of this batch: c = (j0 + k) G + me < 28
+                for (uint32_t j = j0; j < j1; j++) {
+                    const uint32_t c = j * G + me;
+                    if (c >= kWidth) break;
+                    own++;
                     if (host_columns) {
                         if (staged)
                             staged_copy_column(d_trace_in + (size_t)c * n, host_columns[c], n * 16, chunk);
                         else
                             EZK_CUDA(cudaMemcpyAsync(d_trace_in + (size_t)c * n, host_columns[c], n * 16, cudaMemcpyHostToDevice, copy_stream_));
-                        EZK_CUDA(cudaEventRecord(copy_ev_[j % 14], copy_stream_));
-                        EZK_CUDA(cudaStreamWaitEvent(stream_, copy_ev_[j % 14], 0));
                     }
-                    if (first) mark(), first = false;
-                    check_canonical(stream_, src, n, d_flag_);
-                    ntt_columns(tables_, stream_, src, n, d_tcoef + (size_t)c * n, n, d_tmp, 1, log_n, true, &sc);
-                } else if (first) {
-                    mark(), first = false;
                 }
-                EZK_CUDA(cudaEventRecord(share_ev_[2 * j], stream_));
-                EZK_CUDA(cudaStreamWaitEvent(aux_stream_, share_ev_[2 * j], 0));
-                comm_.all_gather(d_tcoef + (size_t)c * n, d_tcoef + (size_t)j * G * n, n * 16, aux_stream_);
-                count_launch();
-                EZK_CUDA(cudaEventRecord(share_ev_[2 * j + 1], aux_stream_));
+                if (host_columns) {
+                    EZK_CUDA(cudaEventRecord(copy_ev_[(j0 / rb) % 14], copy_stream_));
+                    EZK_CUDA(cudaStreamWaitEvent(stream_, copy_ev_[(j0 / rb) % 14], 0));
+                }
+                if (mark_pending) mark(), mark_pending = false;
+                if (own) {
+                    const size_t first = (size_t)(j0 * G + me) * n;
+                    for (uint32_t k = 0; k < own; k++) check_canonical(stream_, own_src + first + (size_t)k * G * n, n, d_flag_);
+                    ntt_columns(tables_, stream_, own_src + first, (uint64_t)G * n, d_tcoef + first, (uint64_t)G * n, d_tmp, own, log_n, true, &sc);
+                }
+                EZK_CUDA(cudaEventRecord(share_ev_[2 * j0], stream_));
+                EZK_CUDA(cudaStreamWaitEvent(aux_stream_, share_ev_[2 * j0], 0));
+                for (uint32_t j = j0; j < j1; j++) {
+                    comm_.all_gather(d_tcoef + (size_t)(j * G + me) * n, d_tcoef + (size_t)j * G * n, n * 16, aux_stream_);
+                    count_launch();
+                    EZK_CUDA(cudaEventRecord(share_ev_[2 * j + 1], aux_stream_));
+                }
+                if (j0 >= rb) extend_batch(j0 - rb);
             }
-            for (uint32_t j = 0; j < rounds; j++) {
-                EZK_CUDA(cudaStreamWaitEvent(stream_, share_ev_[2 * j + 1], 0));
-                const size_t c0 = (size_t)j * G;
-                const uint32_t cols = std::min<uint32_t>(G, kWidth - (uint32_t)c0);
-                lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L, L, d_tmp, cols, log_n, cs);
-            }
+            extend_batch(((rounds - 1) / rb) * rb);
         } else if (host_columns) {
             // Upload and transform in column groups: the copy of group k+1 (copy stream) overlaps the
             // interpolation + LDE of group k (compute stream).  Columns are independent until the row hash.
@@ -566,7 +588,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         h2d(d_params_, &hp, sizeof(hp));
         EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[1], 0));
         // sharded: one contiguous array per owned coset, which is what the per-coset interpolation below reads
-        evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L, log_L, d_params_, d_bden, d_combined, sh, sharded);
+        evaluate_constraints(stream_, tables_.root_fwd, d_tlde, L_local, log_L, d_params_, d_bden, d_combined, sh, sharded);
     }
     mark();
 
@@ -607,7 +629,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         if (flag)
             throw ProveFailure{EZK_ERR_CONSTRAINT_DEGREE,
                                "constraint composition polynomial has degree >= 7n: the trace does not satisfy the AIR"};
-        lde_columns(tables_, stream_, d_ccoef, n, d_clde, L, d_tmp, kCompCols, log_n, cs);
+        lde_columns(tables_, stream_, d_ccoef, n, d_clde, L_local, d_tmp, kCompCols, log_n, cs);
         last_.comp_root = commit(d_clde, kCompCols, L, d_cnodes, comp_tree);
         commitments.insert(commitments.end(), last_.comp_root.begin(), last_.comp_root.end());
         coin.reseed(last_.comp_root);
@@ -684,7 +706,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         if (sharded) {
             // the pointwise formula on the rows this rank owns: no communication
             EZK_CUDA(cudaStreamWaitEvent(stream_, aux_ev_[3], 0));
-            deep_from_rows(stream_, tables_.root_fwd, d_tlde, L, d_clde, L, log_L, d_dc, d_invden, ds, d_deep_local, sh);
+            deep_from_rows(stream_, tables_.root_fwd, d_tlde, L_local, d_clde, L_local, log_L, d_dc, d_invden, ds, d_deep_local, sh);
         } else {
             deep_combine_coeffs(stream_, d_tcoef, n, d_ccoef, n, log_n, d_dc, d_pq);
             lde_columns(tables_, stream_, d_pq, n, d_pqlde, L, d_tmp, 2, log_n, cs);
@@ -821,15 +843,14 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     ops.reserve(2 + nlayers);
     std::vector<uint64_t> flat;
     size_t out_units = 0;
-    // rows_mode 0: whole table on this rank; 1: rows owned by p mod G at index p (LDE tables keep the global row index);
-    // 2: rows owned by p mod G at index p / G (packed FRI layer)
+    // rows_mode 0: whole table on this rank; 1: row p is owned by rank p mod G and sits at index p / G there (packed)
     auto plan_opening = [&](const uint4* table, uint64_t pitch, uint32_t width, const ShardTree* tree, int rows_mode,
                             const std::vector<uint64_t>& pos) {
         Opening op{table, pitch, width, tree, pos, {}, batch_proof_node_indices(tree->leaves, pos), {}, {}, flat.size(), 0, out_units};
         for (uint64_t p : pos) {
             const uint32_t owner = rows_mode == 0 ? me : (uint32_t)(p & (G - 1));
             op.row_owner.push_back(owner);
-            flat.push_back(owner != me ? 0 : rows_mode == 2 ? p >> glog : p);
+            flat.push_back(owner != me ? 0 : rows_mode == 1 ? p >> glog : p);
         }
         for (auto& v : op.idx_lists)
             for (uint64_t k : v) {
@@ -848,14 +869,14 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         out_units += pos.size() * width + 2 * op.ndig;
         ops.push_back(std::move(op));
     };
-    plan_opening(d_tlde, L, kWidth, &trace_tree, sharded ? 1 : 0, positions);
-    plan_opening(d_clde, L, kCompCols, &comp_tree, sharded ? 1 : 0, positions);
+    plan_opening(d_tlde, L_local, kWidth, &trace_tree, sharded ? 1 : 0, positions);
+    plan_opening(d_clde, L_local, kCompCols, &comp_tree, sharded ? 1 : 0, positions);
     {
         std::vector<uint64_t> pos = positions;
         for (auto& layer : layers) {
             pos = fold_positions(pos, layer.size, 8);
             const uint64_t m = layer.size / 8;
-            plan_opening(layer.evals, layer.packed ? m >> glog : m, 8, &layer.tree, layer.packed ? 2 : 0, pos);
+            plan_opening(layer.evals, layer.packed ? m >> glog : m, 8, &layer.tree, layer.packed ? 1 : 0, pos);
         }
     }
     const bool exchange = sharded && G > 1;
