@@ -2,6 +2,7 @@
 #include "merkle.cuh"
 #include "../common.h"
 #include "../hash/blake3.cuh"
+#include <algorithm>
 
 namespace ezk {
 
@@ -54,15 +55,33 @@ __global__ void unpack_rows_kernel(const uint4* __restrict__ src, uint64_t per_r
     for (int u = 0; u < UNITS; u++) dst[i * UNITS + u] = src[g * UNITS + u];
 }
 
-// parents k in [level, 2*level): nodes[k] = merge(nodes[2k], nodes[2k+1])
-__global__ void __launch_bounds__(kThreads) merkle_level_kernel(uint4* __restrict__ nodes, uint64_t level) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= level) return;
-    uint64_t k = level + t;
+// `depth` (<= 9) levels per launch: CTA b merges the 512 digests under parents [256 b, 256 b + 256) of the level with
+// `level` parents, keeps the results in shared memory and goes on with the 128, 64, ... parents above them; every level
+// is also written to the node array.  level must be a multiple of 256.
+__global__ void __launch_bounds__(kThreads) merkle_subtree_kernel(uint4* __restrict__ nodes, uint64_t level, int depth) {
+    __shared__ uint4 sm[2][2 * kThreads];
+    const uint32_t t = threadIdx.x;
     uint4 out[2];
-    b3_merge(nodes + 4 * k, out);  // children 2k, 2k+1 are 64 contiguous bytes at digest index 2k
-    nodes[2 * k] = out[0];
-    nodes[2 * k + 1] = out[1];
+    {
+        const uint64_t k = level + (uint64_t)blockIdx.x * kThreads + t;
+        b3_merge(nodes + 4 * k, out);
+        nodes[2 * k] = out[0], nodes[2 * k + 1] = out[1];
+        sm[0][2 * t] = out[0], sm[0][2 * t + 1] = out[1];
+    }
+    __syncthreads();
+    uint32_t width = kThreads;
+    int cur = 0;
+    for (int d = 1; d < depth; d++) {
+        level >>= 1, width >>= 1;
+        if (t < width) {
+            b3_merge(&sm[cur][4 * t], out);
+            const uint64_t k = level + (uint64_t)blockIdx.x * width + t;
+            nodes[2 * k] = out[0], nodes[2 * k + 1] = out[1];
+            sm[cur ^ 1][2 * t] = out[0], sm[cur ^ 1][2 * t + 1] = out[1];
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
 }
 
 // finishes the tree from `level` (<= 1024 parents) down to the root inside one CTA
@@ -136,14 +155,17 @@ int unpack_rows(cudaStream_t s, const uint4* gathered, uint64_t per_rank, uint32
 int merkle_build(cudaStream_t s, uint4* nodes, uint64_t num_leaves) {
     int launches = 0;
     uint64_t level = num_leaves / 2;
-    for (; level > 1024; level >>= 1) {
-        unsigned blocks = (unsigned)((level + kThreads - 1) / kThreads);
+    while (level > 1024) {
+        // up to 9 levels per launch (a CTA carries its 256 parents up through shared memory); the last 1024 parents
+        // and everything above them belong to the single-CTA top kernel
+        const int depth = (int)std::min<unsigned>(9, ilog2_u64(level) - 10);
         {
-            LaunchScope ls(s, K_MERKLE_LEVEL, level * 96);
-            merkle_level_kernel<<<blocks, kThreads, 0, s>>>(nodes, level);
+            LaunchScope ls(s, K_MERKLE_LEVEL, level * 96 * 2);
+            merkle_subtree_kernel<<<(unsigned)(level / kThreads), kThreads, 0, s>>>(nodes, level, depth);
         }
         EZK_CUDA(cudaGetLastError());
         launches++;
+        level >>= depth;
     }
     if (level >= 1) {
         {

@@ -423,7 +423,8 @@ struct FinalArgs {
     uint32_t passes;                // p in {1,2,3}
     uint32_t log_top;               // log2(n_p), the most significant storage digit (p >= 2)
     uint32_t mode;                  // 0 plain, 1 LDE from tmp (lanes = cosets), 2 LDE direct from coefficients (p = 1)
-    uint32_t lanes_log;             // 0 (one run per tile), 2 or 3
+    uint32_t lanes_log;             // log2(runs handled side by side by one CTA)
+    uint32_t lanes_c_log;           // LDE: the low lanes_c_log lane bits select a coset, the bits above an adjacent run (j_p)
     uint32_t log_L;
     uint32_t inv;
     uint32_t cs_log, cs_base, cs_step;  // LDE: 1 << cs_log cosets are computed, coset k = cs_base + cs_step * k
@@ -457,8 +458,9 @@ struct FinalPass {
         if (a->mode == 0) {
             in.ptr = src + ((run0 + lane * run_step) << a->log_s) + i0;
         } else if (a->mode == 1) {
-            // coset0 + lane = index into this prover's coset list; the coset itself is cs_base + cs_step * index
-            in.ptr = src + (uint64_t)(coset0 + lane) * a->src_pitch + (run0 << a->log_s) + i0;
+            // coset0 + lc = index into this prover's coset list; the coset itself is cs_base + cs_step * index
+            const uint32_t lc = lane & ((1u << a->lanes_c_log) - 1), lj = lane >> a->lanes_c_log;
+            in.ptr = src + (uint64_t)(coset0 + lc) * a->src_pitch + ((run0 + lj * run_step) << a->log_s) + i0;
         } else {
             in.ptr = src + i0;
             in.coset = a->cs_base + a->cs_step * (coset0 + lane);
@@ -478,7 +480,8 @@ struct FinalPass {
             out.step = 1ull << (log_s - 3 + log_H);
         } else {
             // packed row order: the rows of the cosets this prover computes, ascending (all 8 cosets: the natural order)
-            out.index = ((((uint64_t)jg << log_H) + out_base) << a->cs_log) + coset0 + lane;
+            const uint32_t lc = lane & ((1u << a->lanes_c_log) - 1), lj = lane >> a->lanes_c_log;
+            out.index = ((((uint64_t)jg << log_H) + out_base + lj) << a->cs_log) + coset0 + lc;
             out.step = 1ull << (log_s - 3 + log_H + a->cs_log);
         }
         out.ptr = dst + out.index;
@@ -524,18 +527,25 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_final_pass(const __grid_con
             P.out_base = (rest << a.log_top) + jp0;  // j_p + n_p * rest
         }
     } else {
-        // LDE: one run per tile, the lanes are cosets (all of this prover's, or a part of them)
-        const uint32_t halves_log = a.cs_log - a.lanes_log;
-        const uint64_t hp = blockIdx.x >> halves_log;
-        P.coset0 = (blockIdx.x & ((1u << halves_log) - 1)) << a.lanes_log;
-        P.run0 = hp, P.run_step = 0;
+        // LDE: the lanes are cosets (all of this prover's, or a part of them) and, when a prover computes fewer cosets
+        // than a tile has lanes (multi-GPU), adjacent runs j_p as in the plain transform: either way the lanes of a
+        // tile write adjacent rows of the packed output
+        const uint32_t lj_log = a.lanes_log - a.lanes_c_log;
+        const uint32_t halves_log = a.cs_log - a.lanes_c_log;
+        const uint64_t hp = blockIdx.x >> halves_log;  // run tile
+        P.coset0 = (blockIdx.x & ((1u << halves_log) - 1)) << a.lanes_c_log;
         P.src = a.mode == 1 ? a.src + (((uint64_t)col * a.src_pitch) << a.cs_log) : a.src + (uint64_t)col * a.src_pitch;
         if (a.passes <= 1) {
-            P.out_base = 0;
+            P.run0 = hp, P.run_step = 0, P.out_base = 0;
         } else {
+            // consecutive CTAs take consecutive `rest`, i.e. read adjacent runs (measured: 6 % faster at 2^20 than the
+            // order that makes their outputs adjacent)
             const uint32_t log_rest = P.log_H - a.log_top;
-            const uint64_t rest = hp & ((1ull << log_rest) - 1), jp = hp >> log_rest;
-            P.out_base = (rest << a.log_top) + jp;
+            const uint64_t rest = hp & ((1ull << log_rest) - 1);
+            const uint32_t jp0 = (uint32_t)(hp >> log_rest) << lj_log;
+            P.run0 = rest + ((uint64_t)jp0 << log_rest);
+            P.run_step = 1ull << log_rest;
+            P.out_base = (rest << a.log_top) + jp0;  // j_p + n_p * rest
         }
     }
     tile_transform<INV>(P, tile, a.log_s, a.lanes_log, a.tw);
@@ -558,44 +568,45 @@ __global__ void ntt_tiny_kernel(const uint4* src, uint64_t src_pitch, uint4* dst
     fe_store(dst + (uint64_t)col * dst_pitch + j, acc);
 }
 
-// Composition columns from per-coset interpolations (multi-GPU).  y holds, for each of the 8 LDE cosets c,
-// the plain inverse transform (no 1/n) Y_c of the n constraint evaluations on that coset, as the all-gathered blocks
-// of the ranks: coset c = q + world * k is array (q * (8 / world) + k).  With H'_j[m] = 3^m H_j[m]:
+// Composition columns from per-coset interpolations (multi-GPU).  For each of the 8 LDE cosets c, Y_c is the
+// plain inverse transform (no 1/n) of the n constraint evaluations on that coset.  With H'_j[m] = 3^m H_j[m]:
 //     Y_c[m] = n w_L^(cm) sum_j (3^n w_8^c)^j H'_j[m]   =>   H'_j[m] = s_j sum_c w_8^(-cj) w_L^(-cm) Y_c[m],  s_j = 3^(-nj) / L
-// out[j][m] for j < 7; *flag |= 1 when an H'_7[m] is non-zero (composition degree >= 7n).
+// A rank handles the coefficient slice m in [m0, m0 + count): y[c * count + (m - m0)] in, out[j * count + (m - m0)] for
+// j < 7 out; *flag |= 1 when an H'_7[m] is non-zero (composition degree >= 7n).
 struct RecombineConsts {
     uint64_t s[8][2];
 };
-__global__ void __launch_bounds__(128) composition_recombine_kernel(const uint4* __restrict__ y, uint32_t log_n, uint32_t world_log,
-                                                                   const uint4* __restrict__ root_inv, RecombineConsts k,
-                                                                   uint4* __restrict__ out, uint32_t* __restrict__ flag) {
-    const uint64_t n = 1ull << log_n;
-    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n) return;
-    Arith<false> ar;
-    const uint32_t cn_log = 3 - world_log;
-    const fe u = fe_root_pow(root_inv, log_n + 3, m);  // w_L^-m
-    fe x[8];
+template <class AR>
+__device__ __forceinline__ bool recombine_point(const uint4* __restrict__ y, uint64_t count, uint64_t at, const fe& u,
+                                                const RecombineConsts& k, fe (&x)[8]) {
+    AR ar;
     fe p = u;
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) {
-        const uint32_t q = c & ((1u << world_log) - 1), kk = c >> world_log;
-        fe v = fe_ldg(y + ((uint64_t)((q << cn_log) + kk) << log_n) + m);
+        fe v = fe_ldg(y + c * count + at);
         if (c > 0) {
-            v = fe_mul(v, p);
-            if (c < 7) p = fe_mul(p, u);
+            v = ar.mul(v, p);
+            if (c < 7) p = ar.mul(p, u);
         }
         x[c] = v;
     }
     dft8<1>(ar, x);
 #pragma unroll
-    for (uint32_t j = 0; j < 8; j++) {
-        const fe v = fe_mul(x[j], fe_make(k.s[j][0], k.s[j][1]));
-        if (j < 7)
-            fe_store(out + ((uint64_t)j << log_n) + m, v);
-        else if (!fe_is_zero(v))
-            atomicOr(flag, 1u);
-    }
+    for (uint32_t j = 0; j < 8; j++) x[j] = ar.mul(x[j], fe_make(k.s[j][0], k.s[j][1]));
+    return ar.tainted();
+}
+__global__ void __launch_bounds__(128) composition_recombine_kernel(const uint4* __restrict__ y, uint32_t log_n, uint64_t m0,
+                                                                   uint64_t count, const uint4* __restrict__ root_inv,
+                                                                   RecombineConsts k, uint4* __restrict__ out,
+                                                                   uint32_t* __restrict__ flag) {
+    const uint64_t at = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (at >= count) return;
+    const fe u = fe_root_pow(root_inv, log_n + 3, m0 + at);  // w_L^-m
+    fe x[8];
+    if (recombine_point<Arith<true>>(y, count, at, u, k, x)) recombine_point<Arith<false>>(y, count, at, u, k, x);
+#pragma unroll
+    for (uint32_t j = 0; j < 7; j++) fe_store(out + j * count + at, x[j]);
+    if (!fe_is_zero(x[7])) atomicOr(flag, 1u);
 }
 
 size_t tile_bytes(uint32_t log_s, uint32_t lanes_log) { return (((size_t)1 << log_s) << lanes_log) * sizeof(uint4); }
@@ -923,14 +934,13 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
     return launches + 1;
 }
 
-int composition_recombine(const NttTables& t, cudaStream_t s, const uint4* y, uint32_t log_n, uint32_t world_log,
+int composition_recombine(const NttTables& t, cudaStream_t s, const uint4* y, uint32_t log_n, uint64_t m0, uint64_t count,
                           const uint64_t scale[8][2], uint4* out, uint32_t* flag) {
     RecombineConsts k;
     for (int j = 0; j < 8; j++) k.s[j][0] = scale[j][0], k.s[j][1] = scale[j][1];
-    const uint64_t n = 1ull << log_n;
     {
-        LaunchScope ls(s, K_NTT_FINAL, n * 16 * 15);
-        composition_recombine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(y, log_n, world_log, t.root_inv, k, out, flag);
+        LaunchScope ls(s, K_NTT_FINAL, count * 16 * 15);
+        composition_recombine_kernel<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(y, log_n, m0, count, t.root_inv, k, out, flag);
     }
     EZK_CUDA(cudaGetLastError());
     return 1;
@@ -949,7 +959,12 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
     a.dst = lde, a.dst_pitch = lde_pitch;
     a.log_n = log_n, a.log_s = pl.log_d[0], a.passes = pl.passes;
     a.log_top = pl.passes >= 2 ? pl.log_d[pl.passes - 1] : 0;
-    a.lanes_log = lanes_log_for(a.log_s) > cs.count_log ? cs.count_log : lanes_log_for(a.log_s);  // lanes are cosets
+    // lanes: this prover's cosets first, then adjacent runs until the tile is full
+    const uint32_t lanes_want = lanes_log_for(a.log_s);
+    a.lanes_c_log = lanes_want > cs.count_log ? cs.count_log : lanes_want;
+    uint32_t lanes_j_log = pl.passes >= 2 ? lanes_want - a.lanes_c_log : 0;
+    if (lanes_j_log > a.log_top) lanes_j_log = a.log_top;
+    a.lanes_log = a.lanes_c_log + lanes_j_log;
     a.cs_log = cs.count_log, a.cs_base = cs.base, a.cs_step = cs.step;
     a.log_L = log_L;
     a.inv = 0;
@@ -964,7 +979,7 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
         a.mode = 1;
         a.src = tmp, a.src_pitch = n;
     }
-    dim3 grid((unsigned)((1ull << (log_n - pl.log_d[0])) << (cs.count_log - a.lanes_log)), ncols);
+    dim3 grid((unsigned)(((1ull << (log_n - pl.log_d[0])) >> lanes_j_log) << (cs.count_log - a.lanes_c_log)), ncols);
     {
         const uint64_t elems = (uint64_t)ncols << log_n, outs = elems << cs.count_log;
         LaunchScope ls(s, K_NTT_FINAL, (pl.passes == 1 ? elems + outs : 2 * outs) * 16);

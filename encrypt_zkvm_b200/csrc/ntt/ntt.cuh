@@ -68,10 +68,11 @@ struct CosetSet {
 int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t coeff_pitch, uint4* lde,
                 uint64_t lde_pitch, uint4* tmp, uint32_t ncols, uint32_t log_n, CosetSet cs = CosetSet());
 
-// Multi-GPU composition step: the 7 composition columns (offset-scaled coefficients, pitch n) from the plain inverse
-// transforms of the constraint evaluations on each of the 8 LDE cosets (see composition_recombine_kernel).
-// scale[j] = 3^(-nj) / L.  *flag |= 1 when the eighth column is not identically zero.
-int composition_recombine(const NttTables& t, cudaStream_t s, const uint4* y, uint32_t log_n, uint32_t world_log,
+// Multi-GPU composition step: a slice [m0, m0 + count) of the 7 composition columns (offset-scaled coefficients) from
+// the same slice of the plain inverse transforms of the constraint evaluations on each of the 8 LDE cosets
+// (y[c * count + k], out[j * count + k]; see composition_recombine_kernel).  scale[j] = 3^(-nj) / L.
+// *flag |= 1 when the eighth column is not identically zero on the slice.
+int composition_recombine(const NttTables& t, cudaStream_t s, const uint4* y, uint32_t log_n, uint64_t m0, uint64_t count,
                           const uint64_t scale[8][2], uint4* out, uint32_t* flag);
 
 }  // namespace ezk

@@ -604,12 +604,17 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         uint32_t flag = 0;
         if (sharded) {
             // C(x) = sum_j x^(jn) H_j(x) restricted to coset c is R_c(x) = sum_j (3^n w_8^c)^j H_j(x), degree < n: every
-            // rank interpolates its cosets, the 8 coefficient arrays are all-gathered, and an 8-point inverse DFT across
-            // the cosets separates the H_j (see composition_recombine_kernel)
+            // rank interpolates its cosets; an all-to-all hands rank q the coefficient slice [q n / G, (q + 1) n / G) of
+            // all 8 cosets, where an 8-point inverse DFT across the cosets separates the H_j (composition_recombine);
+            // the slices of column j are then all-gathered (auxiliary stream) while column j - 1 is being extended
+            const uint64_t slice = n >> glog;
             ntt_columns(tables_, stream_, d_combined, n, d_rloc, n, d_tmp, cn, log_n, true, nullptr);
-            comm_.all_gather(d_rloc, d_rall, (size_t)cn * n * 16, stream_);
-            count_launch();
-            composition_recombine(tables_, stream_, d_rall, log_n, glog, scale8, d_ccoef, d_flag_);
+            for (uint32_t k = 0; k < cn; k++) {  // coset me + G k of this rank -> array me + G k of every rank's slice set
+                comm_.all_to_all(d_rloc + (size_t)k * n, d_rall + (size_t)k * n, slice * 16, stream_);
+                count_launch();
+            }
+            // d_rall[(k G + q) * slice ..] = coset q + G k: natural coset order, one slice each; d_rloc is free again
+            composition_recombine(tables_, stream_, d_rall, log_n, (uint64_t)me * slice, slice, scale8, d_rloc, d_flag_);
             uint32_t* d_flags = reinterpret_cast<uint32_t*>(d_small + 2048);
             comm_.all_gather(d_flag_, d_flags, sizeof(uint32_t), stream_);  // every rank takes the same decision
             count_launch();
@@ -629,7 +634,24 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         if (flag)
             throw ProveFailure{EZK_ERR_CONSTRAINT_DEGREE,
                                "constraint composition polynomial has degree >= 7n: the trace does not satisfy the AIR"};
-        lde_columns(tables_, stream_, d_ccoef, n, d_clde, L_local, d_tmp, kCompCols, log_n, cs);
+        if (sharded) {
+            const uint64_t slice = n >> glog;
+            EZK_CUDA(cudaEventRecord(share_ev_[0], stream_));
+            EZK_CUDA(cudaStreamWaitEvent(aux_stream_, share_ev_[0], 0));
+            for (uint32_t j = 0; j < kCompCols; j++) {
+                comm_.all_gather(d_rloc + (size_t)j * slice, d_ccoef + (size_t)j * n, slice * 16, aux_stream_);
+                count_launch();
+                EZK_CUDA(cudaEventRecord(share_ev_[1 + j], aux_stream_));
+            }
+            const uint32_t cuts[4] = {0, 2, 4, kCompCols};  // extension launches of 2, 2 and 3 columns
+            for (int b = 0; b < 3; b++) {
+                EZK_CUDA(cudaStreamWaitEvent(stream_, share_ev_[cuts[b + 1]], 0));
+                lde_columns(tables_, stream_, d_ccoef + (size_t)cuts[b] * n, n, d_clde + (size_t)cuts[b] * L_local, L_local, d_tmp,
+                            cuts[b + 1] - cuts[b], log_n, cs);
+            }
+        } else {
+            lde_columns(tables_, stream_, d_ccoef, n, d_clde, L_local, d_tmp, kCompCols, log_n, cs);
+        }
         last_.comp_root = commit(d_clde, kCompCols, L, d_cnodes, comp_tree);
         commitments.insert(commitments.end(), last_.comp_root.begin(), last_.comp_root.end());
         coin.reseed(last_.comp_root);
