@@ -302,34 +302,52 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     uint64_t shard_fri_min_rows = 4096;             // FRI layers with fewer rows are gathered and finished on every rank
     if (const char* e = getenv("EZK_SHARD_FRI_MIN_ROWS")) shard_fri_min_rows = std::max<uint64_t>(64, (uint64_t)atoll(e));
 
-    // ---- workspace ----
+    // trace columns per interpolation + extension launch of a device-resident trace: the transform scratch is sized by
+    // the group, which is what lets a 2^24-row proof fit one GPU (EZK_LDE_GROUP overrides)
+    uint32_t lde_group = log_n >= 23 ? 4 : kWidth;
+    if (const char* e = getenv("EZK_LDE_GROUP")) lde_group = (uint32_t)std::min<long>(kWidth, std::max<long>(1, atol(e)));
+
+    // ---- workspace (16-byte elements; the arena is sized once per trace length and kept) ----
+    // transform scratch in columns of L_local elements: sharded batches hold <= 8 columns, the host path 2-column groups,
+    // the DEEP step 2 columns; the composition columns are extended in groups that fit
+    const uint32_t tmp_cols = sharded ? 8 : std::max(2u, host_columns ? 2u : lde_group);
+    const uint32_t comp_group = std::min(kCompCols, tmp_cols);
     size_t fri_elems = 0;
+    uint64_t first_whole_layer = 0;  // sharded: size of the first FRI layer that is gathered onto every rank
     {
         uint64_t s = L;
+        bool packed = sharded;
         for (size_t k = 0; k < nlayers; k++) {
-            fri_elems += s / 8 + 4 * (s / 8) + 64;
+            const uint64_t m = s / 8;
+            if (packed && !(m >= shard_fri_min_rows && m >= (uint64_t)G * G)) packed = false, first_whole_layer = s;
+            fri_elems += s / 8 + 4 * (s / 8) + 64 + (first_whole_layer == s ? s : 0);
             s /= 8;
         }
-        fri_elems += 8192;
+        if (packed) first_whole_layer = s, fri_elems += s;
+        fri_elems += 2 * s + 8192;
     }
-    const size_t need = 2 * kWidth * n + (sharded ? 4 * n : 0) + 2 * kWidth * L + 4 * L + 3 * L + kCompCols * L + 4 * L + 2 * n + 2 * L + L +
-                        4 * L + (sharded ? 6 * L_local + 16 * n + L + 4096 : 0) + (size_t)(2 * kWidth + kCompCols) * eval_blocks + fri_elems +
-                        4 * 65536;
+    const size_t tcoef_cols = sharded ? (size_t)rounds * G : kWidth;
+    const size_t allg_elems = sharded ? std::max<size_t>(first_whole_layer, (size_t)32768 * G) + 64 : 0;
+    const size_t need = (host_columns ? (size_t)kWidth * n : 0) + tcoef_cols * n + (size_t)kWidth * L_local + (size_t)tmp_cols * L_local +
+                        (sharded ? 0 : 8 * L) /* whole trees */ + 3 * L_local + L + (size_t)kCompCols * L_local + 2 * n +
+                        (sharded ? 0 : 2 * L) + (size_t)(2 * kWidth + kCompCols) * eval_blocks + 4096 +
+                        (sharded ? 4 * L_local + (size_t)cn * n + 8 * n + allg_elems + 8 * L_local /* subtrees */ : 0) + fri_elems +
+                        8192 + 32768 + 64 * 32;
     reserve(need);
     reset_arena();
     uint4* d_trace_in = host_columns ? alloc(kWidth * n) : nullptr;
-    uint4* d_tcoef = alloc((size_t)(sharded ? rounds * G : kWidth) * n);
+    uint4* d_tcoef = alloc(tcoef_cols * n);
     uint4* d_tlde = alloc(kWidth * L_local);  // multi-GPU: this rank's rows only, packed order
-    uint4* d_tmp = alloc(kWidth * L);
+    uint4* d_tmp = alloc((size_t)tmp_cols * L_local);
     uint4* d_tnodes = sharded ? nullptr : alloc(4 * L);
-    uint4* d_invden = alloc(L);
-    uint4* d_combined = alloc(L);
+    uint4* d_invden = alloc(L_local);
+    uint4* d_combined = alloc(L_local);
     uint4* d_ccoef = alloc(L);
     uint4* d_clde = alloc(kCompCols * L_local);
     uint4* d_cnodes = sharded ? nullptr : alloc(4 * L);
     uint4* d_pq = alloc(2 * n);
     uint4* d_pqlde = sharded ? nullptr : alloc(2 * L);
-    uint4* d_deep = alloc(L);
+    uint4* d_deep = alloc(L_local);
     uint4* d_scratch = alloc((size_t)(2 * kWidth + kCompCols) * eval_blocks);
     uint4* d_small = alloc(4096);  // OOD outputs, deep coefficients, subtree roots, flags
     // sharded: packed per-row products of this rank, the receive side of the exchanges
@@ -337,7 +355,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     uint4* d_recv = sharded ? alloc(2 * L_local) : nullptr;
     uint4* d_rloc = sharded ? alloc((size_t)cn * n) : nullptr;   // per-coset interpolations of the constraint evaluations
     uint4* d_rall = sharded ? alloc(8 * n) : nullptr;
-    uint4* d_allg = sharded ? alloc(L + 4096) : nullptr;         // gathered FRI evaluations / opened rows of every rank
+    uint4* d_allg = sharded ? alloc(allg_elems) : nullptr;       // gathered FRI evaluations / opened rows of every rank
 
     struct ShardTree {            // Merkle tree of one commitment
         bool split = false;       // false: `nodes` is the whole tree (heap order, node 1 = root)
@@ -492,8 +510,13 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         } else {
             mark();
             check_canonical(stream_, device_trace, kWidth * n, d_flag_);
-            ntt_columns(tables_, stream_, device_trace, n, d_tcoef, n, d_tmp, kWidth, log_n, true, &sc);
-            lde_columns(tables_, stream_, d_tcoef, n, d_tlde, L, d_tmp, kWidth, log_n, cs);
+            // column groups: the coefficient columns of a group (16 MiB each at 2^20) and the inter-pass twiddle table
+            // compete for the L2, and the transform scratch is sized by the group
+            for (uint32_t c0 = 0; c0 < kWidth; c0 += lde_group) {
+                const uint32_t cols = std::min(lde_group, kWidth - c0);
+                ntt_columns(tables_, stream_, device_trace + (size_t)c0 * n, n, d_tcoef + (size_t)c0 * n, n, d_tmp, cols, log_n, true, &sc);
+                lde_columns(tables_, stream_, d_tcoef + (size_t)c0 * n, n, d_tlde + (size_t)c0 * L, L, d_tmp, cols, log_n, cs);
+            }
         }
     }
     mark();
@@ -650,7 +673,9 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
                             cuts[b + 1] - cuts[b], log_n, cs);
             }
         } else {
-            lde_columns(tables_, stream_, d_ccoef, n, d_clde, L_local, d_tmp, kCompCols, log_n, cs);
+            for (uint32_t c0 = 0; c0 < kCompCols; c0 += comp_group)
+                lde_columns(tables_, stream_, d_ccoef + (size_t)c0 * n, n, d_clde + (size_t)c0 * L, L, d_tmp,
+                            std::min(comp_group, kCompCols - c0), log_n, cs);
         }
         last_.comp_root = commit(d_clde, kCompCols, L, d_cnodes, comp_tree);
         commitments.insert(commitments.end(), last_.comp_root.begin(), last_.comp_root.end());
