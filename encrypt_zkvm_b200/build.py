@@ -55,12 +55,17 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the CUDA library cannot be built (there is no CPU fallback)")
 
 
+# EZK_EXTRA_NVCC_FLAGS: extra compile-time defines for A/B measurements (e.g. -DEZK_NTT_PRE_TWIDDLES=0); part of the stamp
+def _extra_flags():
+    return os.environ.get("EZK_EXTRA_NVCC_FLAGS", "").split()
+
+
 def _digest(paths) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):
         h.update(str(p).encode())
         h.update(Path(p).read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -81,7 +86,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     def compile_one(rel: str):
         src = CSRC / rel
         obj = BUILD / (rel.replace("/", "_") + ".o")
-        cmd = [nvcc, "-ccbin", cxx, *NVCC_FLAGS, "-x", "cu", "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, "-ccbin", cxx, *NVCC_FLAGS, *_extra_flags(), "-x", "cu", "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (BUILD / (rel.replace("/", "_") + ".log")).write_text(r.stdout + r.stderr)
         if r.returncode != 0:

@@ -60,12 +60,13 @@ constexpr uint32_t kTwMaxLog = 11;
 // In-tile twiddles in precomputed form: a second set of compact tables holds every twiddle as 4 x 16 bytes
 // (w * 2^(32 i) mod M) and the in-tile twiddle products use fe_mul_pre like the 8-point DFT constants do - 42 instead
 // of 58 instructions per product for 4 x the table bytes (256 KiB per direction, L1/L2 resident) and up to 16 instead
-// of 4 registers per twiddle in flight.  EZK_NTT_PRE_TWIDDLES: 0 off, 1 both passes, 2 the final pass only.  2 is the
-// default: measured on the B200 at 2^20 rows (round-1 end-of-round probes, five proofs each, identical proof bytes)
-// the trace LDE takes 14.1 ms against 15.3-16.5 ms for 0 and 1 - the strided pass sits at its register limit and
-// loses what the shorter product gains.  Which passes use them is the Pass type's kPreTw.
+// of 4 registers per twiddle in flight.  EZK_NTT_PRE_TWIDDLES: 0 off (default), 1 both passes, 2 the final pass only.
+// Measured A/B on one B200, same box, 2^20 rows (profiles/r02_ntt_pre_twiddles_ab.log): 0 -> final pass 7.04 ms,
+// proof 26.7 ms, e2e 29.2 ms; 2 -> 7.40 / 27.1 / 29.7 (the twiddle loads become the top stall: long_scoreboard 3.3
+// warps per issue in ncu); 1 -> strided pass 10.05 -> 11.44 ms.  (The round-1 end-of-round probe that showed 2 ahead
+// did not reproduce.)  Which passes use them is the Pass type's kPreTw.
 #ifndef EZK_NTT_PRE_TWIDDLES
-#define EZK_NTT_PRE_TWIDDLES 2
+#define EZK_NTT_PRE_TWIDDLES 0
 #endif
 // EZK_NTT_PRE_PASS_TABLE=1 (measured in round 1, slower: 512 MiB of table traffic for the 2^20 LDE): the full
 // inter-pass twiddle tables of the strided passes hold their entries in precomputed form as well (64 bytes per entry)
@@ -633,7 +634,7 @@ Plan make_plan(uint32_t log_n, int max_tile_log) {
 }
 
 // launch shapes: 0 = 256 threads x 3 CTAs/SM (<= 85 registers), 1 = 512 threads x 2 CTAs/SM (<= 64 registers)
-int g_variant = -1;
+int g_variant = -1, g_variant_final = 0;
 template <int T, int B, int INV>
 void set_smem_attr() {
     const int bytes = (int)(kTileElems * 16);
@@ -647,6 +648,8 @@ void ensure_smem_attr() {
     set_smem_attr<256, 2, 0>(), set_smem_attr<256, 2, 1>();
     const char* env = getenv("EZK_NTT_VARIANT");
     g_variant = env ? atoi(env) : 0;
+    const char* envf = getenv("EZK_NTT_FINAL_VARIANT");  // launch shape of the final pass alone (measurement knob)
+    g_variant_final = envf ? atoi(envf) : g_variant;
 }
 template <int T, int B>
 void launch_strided_tb(dim3 grid, size_t smem, cudaStream_t s, const StridedArgs& a) {
@@ -673,9 +676,9 @@ void launch_strided(dim3 grid, size_t smem, cudaStream_t s, const StridedArgs& a
         launch_strided_tb<256, 3>(grid, smem, s, a);
 }
 void launch_final(dim3 grid, size_t smem, cudaStream_t s, const FinalArgs& a) {
-    if (g_variant == 1)
+    if (g_variant_final == 1)
         launch_final_tb<512, 2>(grid, smem, s, a);
-    else if (g_variant == 2)
+    else if (g_variant_final == 2)
         launch_final_tb<256, 2>(grid, smem, s, a);
     else
         launch_final_tb<256, 3>(grid, smem, s, a);

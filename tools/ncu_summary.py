@@ -112,7 +112,7 @@ def launch_list(path: str, out: str):
 
 
 KMAP = {"ntt_strided_pass": "ntt_strided_pass", "ntt_final_pass": "ntt_final_pass", "constraint_kernel": "constraints",
-        "hash_rows_kernel": "hash_rows", "merkle_level_kernel": "merkle_level", "pair_inverse_kernel": "pair_inverse",
+        "hash_rows_kernel": "hash_rows", "merkle_level_kernel": "merkle_level", "merkle_subtree_kernel": "merkle_level", "pair_inverse_kernel": "pair_inverse",
         "eval_partial_kernel": "eval_polys", "fri_fold_kernel": "fri_fold", "deep_combine_kernel": "deep_combine",
         "deep_pointwise_kernel": "deep_pointwise"}
 
