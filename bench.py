@@ -359,6 +359,26 @@ def main():
         except Exception as e:  # optional mode: the contract lines above must survive its failure
             pipelined = {"error": f"{type(e).__name__}: {e}"[:200]}
 
+    # ---- N = 1, informational: BASELINE.json configs[1] (scalar program, 2^16 rows) on the same prover ----
+    config1 = None
+    if world == 1 and args.log_n == 20:
+        try:
+            p1, e1 = ezk.synthetic_case(1, 16)
+            t1 = torch.from_numpy(e1.trace().view(np.int64)).to(f"cuda:{local_rank}")
+            with ezk.ExecutionProver(ezk.ProofOptions(), p1.hash(), e1.outputs(), ezk.ServerKey(), device=local_rank) as q:
+                for _ in range(3):
+                    q.prove_device(t1.data_ptr(), 1 << 16)
+                q.timer_start()
+                for _ in range(20):
+                    pr = q.prove_device(t1.data_ptr(), 1 << 16)
+                ms16 = q.timer_stop() / 20
+                q.verify(pr)
+            config1 = {"workload": "BASELINE.json configs[1]: scalar PUSH/READ/ADD/MUL program, 2^16 rows", "ms_per_proof": ms16,
+                       "proofs_per_s": 1e3 / ms16, "verified": True}
+            del t1
+        except Exception as e:
+            config1 = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -427,7 +447,7 @@ def main():
                 "pinned": {"value": args.steps / t_pin, "ms_per_step": t_pin * 1e3 / args.steps}},
         "gpu_launches": launches_total, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "checks": checks,
         "int_pipe_roofline": int_pipe, "stages": stages, "kernels": kernels, "proof_bytes": len(proof_bytes_dev),
-        "single_gpu_same_config": single, "pipelined": pipelined,
+        "single_gpu_same_config": single, "pipelined": pipelined, "config1_2p16": config1,
         "hbm_roofline_proofs_per_s": peak * 1e9 / sum(ab.values()),
     }
     if single:

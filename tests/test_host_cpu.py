@@ -297,3 +297,17 @@ def test_oracle_trace_generator_matches_the_host_vm(oracle):
         prog, ex = ezk.synthetic_case(kind, log_n)
         assert np.array_equal(trace, ex.trace())
         assert pub == prog.hash() + ex.outputs()
+
+
+def test_rust_shim_declares_only_exported_symbols():
+    """rust-shim/src/ffi.rs (the reference-side binding of INTEGRATION.md, as files) names only functions that the
+    header declares and the library exports, and its constants match the header's status codes."""
+    ffi = (ROOT / "rust-shim" / "src" / "ffi.rs").read_text()
+    header = (ROOT / "include" / "ezkvm_prover.h").read_text()
+    fns = re.findall(r"pub fn (ezk_\w+)\(", ffi)
+    assert len(fns) >= 10
+    for name in fns:
+        assert re.search(rf"\b{name}\(", header), name
+        assert hasattr(_lib.lib, name), name
+    for name, value in re.findall(r"pub const (EZK_\w+): c_int = (-?\d+);", ffi):
+        assert getattr(_lib, name) == int(value), name
