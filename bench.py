@@ -312,6 +312,22 @@ def main():
 
     t_e2e, proof_e2e = e2e_arm(trace_np)
     t_pin, proof_pin = e2e_arm(pinned_np)
+    # N = 1, sub-key: the eight bookkeeping columns (clk, op bits, flag, depth) generated on the device from the operation
+    # list instead of uploaded (ezk_prover_prove_ops): 20 columns + one byte per operation cross PCIe
+    e2e_ops = None
+    if world == 1:
+        codes = prog.op_codes()
+        for _ in range(2):
+            p_ops = prover.prove_with_ops(trace_np, codes)
+        w0 = time.time()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            p_ops = prover.prove_with_ops(trace_np, codes)
+        torch.cuda.synchronize()
+        t_ops = time.perf_counter() - t0
+        sampler.window(w0, time.time())
+        e2e_ops = {"value": args.steps / t_ops, "ms_per_step": t_ops * 1e3 / args.steps, "h2d_bytes_per_step": 20 * n * 16 + len(codes),
+                   "identical_bytes": p_ops.to_bytes() == proof_e2e}
     clocks = sampler.stop()
     launches_total = int(sum_over_ranks(float(launches)))
     h2d_step = h2d_bytes if world == 1 else sum(n * 16 for c in range(28) if c % world == rank)
@@ -444,7 +460,8 @@ def main():
         "e2e": {"value": args.steps / t_e2e if ok else None, "unit": UNIT, "h2d_bytes_per_step": h2d_step,
                 "d2h_bytes_per_step": len(proof_e2e), "ms_per_step": t_e2e * 1e3 / args.steps,
                 "host_memory": "pageable (numpy array; staged through the prover's page-locked ring)",
-                "pinned": {"value": args.steps / t_pin, "ms_per_step": t_pin * 1e3 / args.steps}},
+                "pinned": {"value": args.steps / t_pin, "ms_per_step": t_pin * 1e3 / args.steps},
+                "bookkeeping_columns_on_device": e2e_ops},
         "gpu_launches": launches_total, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "checks": checks,
         "int_pipe_roofline": int_pipe, "stages": stages, "kernels": kernels, "proof_bytes": len(proof_bytes_dev),
         "single_gpu_same_config": single, "pipelined": pipelined, "config1_2p16": config1,

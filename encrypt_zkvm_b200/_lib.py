@@ -44,6 +44,10 @@ class EzkWireCompat(C.Structure):
                 ("trace_info_aux_rands_byte", C.c_uint32), ("reserved", C.c_uint32), ("first_nonce", C.c_uint64)]
 
 
+class EzkOpList(C.Structure):
+    _fields_ = [("codes", C.c_void_p), ("count", C.c_uint64), ("last_row", C.c_void_p)]
+
+
 class EzkTrace(C.Structure):
     _fields_ = [("columns", C.POINTER(C.c_void_p)), ("width", C.c_uint32), ("length", C.c_uint64)]
 
@@ -65,6 +69,8 @@ SIGNATURES = {
     "ezk_prover_destroy": (None, [_P]),
     "ezk_prover_prove": (C.c_int, [_P, C.POINTER(EzkTrace), C.POINTER(EzkPublicInputs), C.POINTER(EzkOptions),
                                    C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    "ezk_prover_prove_ops": (C.c_int, [_P, C.POINTER(EzkTrace), C.POINTER(EzkOpList), C.POINTER(EzkPublicInputs),
+                                       C.POINTER(EzkOptions), C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "ezk_prover_prove_device": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(EzkPublicInputs), C.POINTER(EzkOptions),
                                           C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "ezk_prove": (C.c_int, [C.POINTER(EzkTrace), C.POINTER(EzkPublicInputs), C.POINTER(EzkOptions), C.POINTER(_P),

@@ -30,6 +30,7 @@ SOURCES = [
     "merkle/merkle.cu",
     "air/constraints.cu",
     "compose/compose.cu",
+    "trace/expand.cu",
     "fri/fri.cu",
     "host/transcript.cc",
     "host/vm.cc",

@@ -4,6 +4,7 @@
 #include "common.h"
 #include "host/vm.h"
 #include "prover.h"
+#include "trace/expand.cuh"
 #include <algorithm>
 #include <cstring>
 #include <memory>
@@ -169,6 +170,21 @@ int ezk_prover_prove(ezk_prover* p, const ezk_trace* trace, const ezk_public_inp
             if (!trace->columns[c]) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null trace column"};
         std::lock_guard<std::mutex> lock(p->mu);
         auto bytes = p->impl->prove(trace->columns, nullptr, trace->length, to_public(pub), to_options(opt));
+        export_proof(bytes, proof, proof_len);
+    });
+}
+
+int ezk_prover_prove_ops(ezk_prover* p, const ezk_trace* trace, const ezk_op_list* ops, const ezk_public_inputs* pub,
+                         const ezk_options* opt, uint8_t** proof, size_t* proof_len) {
+    return guarded([&] {
+        if (!p || !trace || !ops || !proof || !proof_len || !trace->columns) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null argument"};
+        if (trace->width != EZK_TRACE_WIDTH) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "trace width must be 28"};
+        for (uint32_t c = 0; c < trace->width; c++)
+            if (!trace->columns[c] && !is_op_column(c)) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "null trace column"};
+        OpList ol;
+        ol.codes = ops->codes, ol.count = ops->count, ol.last_row = reinterpret_cast<const uint8_t*>(ops->last_row);
+        std::lock_guard<std::mutex> lock(p->mu);
+        auto bytes = p->impl->prove(trace->columns, nullptr, trace->length, to_public(pub), to_options(opt), &ol);
         export_proof(bytes, proof, proof_len);
     });
 }

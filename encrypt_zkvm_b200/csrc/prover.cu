@@ -10,6 +10,7 @@
 #include "fri/fri.cuh"
 #include "host/air_host.h"
 #include "merkle/merkle.cuh"
+#include "trace/expand.cuh"
 #include <algorithm>
 #include <atomic>
 #include <cstring>
@@ -139,7 +140,7 @@ bool GpuProver::use_staged_upload(const uint8_t* const* host_columns) {
     const char* v = getenv("EZK_STAGED_UPLOAD");  // read per proof: tests switch it inside one process
     if (v && v[0] == '0') return false;
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, host_columns[0]) != cudaSuccess) {
+    if (cudaPointerGetAttributes(&attr, host_columns[7]) != cudaSuccess) {  // column 7 always comes from the caller
         cudaGetLastError();  // older drivers report unregistered memory as an error: that is the pageable case
     } else if (attr.type != cudaMemoryTypeUnregistered) {
         return false;  // page-locked or managed: the plain asynchronous copy already overlaps
@@ -258,9 +259,9 @@ uint4* GpuProver::alloc(size_t elems) {
 void GpuProver::sync() { EZK_CUDA(cudaStreamSynchronize(stream_)); }
 
 std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
-                                      const PublicInputs& pub, const ProofOptions& opt) {
+                                      const PublicInputs& pub, const ProofOptions& opt, const OpList* ops) {
     try {
-        return prove_impl(host_columns, device_trace, n, pub, opt);
+        return prove_impl(host_columns, device_trace, n, pub, opt, ops);
     } catch (...) {
         comm_.abort();  // in-process group: release the peers waiting in a collective
         throw;
@@ -268,7 +269,9 @@ std::vector<uint8_t> GpuProver::prove(const uint8_t* const* host_columns, const 
 }
 
 std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
-                                           const PublicInputs& pub, const ProofOptions& opt) {
+                                           const PublicInputs& pub, const ProofOptions& opt, const OpList* ops) {
+    if (ops && (!host_columns || !ops->codes || !ops->last_row || ops->count >= n))
+        throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "operation list: needs host columns, codes, the last row and count < trace length"};
     if (opt.field_ext != 1) throw ProveFailure{EZK_ERR_UNSUPPORTED_FIELD_EXTENSION, "only FieldExtension::None is supported"};
     if (opt.blowup != 8 || opt.fri_fold != 8)
         throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "blowup factor and FRI folding factor must both be 8"};
@@ -332,7 +335,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
                         (sharded ? 0 : 8 * L) /* whole trees */ + 3 * L_local + L + (size_t)kCompCols * L_local + 2 * n +
                         (sharded ? 0 : 2 * L) + (size_t)(2 * kWidth + kCompCols) * eval_blocks + 4096 +
                         (sharded ? 4 * L_local + (size_t)cn * n + 8 * n + allg_elems + 8 * L_local /* subtrees */ : 0) + fri_elems +
-                        8192 + 32768 + 64 * 32;
+                        8192 + 32768 + 64 * 32 + (ops ? n / 16 + n / 4096 + 128 : 0);
     reserve(need);
     reset_arena();
     uint4* d_trace_in = host_columns ? alloc(kWidth * n) : nullptr;
@@ -350,6 +353,8 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     uint4* d_deep = alloc(L_local);
     uint4* d_scratch = alloc((size_t)(2 * kWidth + kCompCols) * eval_blocks);
     uint4* d_small = alloc(4096);  // OOD outputs, deep coefficients, subtree roots, flags
+    uint8_t* d_codes = ops ? reinterpret_cast<uint8_t*>(alloc(n / 16 + 1)) : nullptr;
+    uint32_t* d_scan = ops ? reinterpret_cast<uint32_t*>(alloc(n / 4096 + 64)) : nullptr;
     // sharded: packed per-row products of this rank, the receive side of the exchanges
     uint4* d_pack = sharded ? alloc(2 * L_local) : nullptr;
     uint4* d_recv = sharded ? alloc(2 * L_local) : nullptr;
@@ -421,6 +426,13 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     // ---- (1) trace upload, interpolation, LDE, commitment ----
     mark();
     EZK_CUDA(cudaMemsetAsync(d_flag_, 0, sizeof(uint32_t), stream_));
+    auto uploaded = [&](uint32_t c) { return !(ops && is_op_column(c)); };  // columns that come from the caller's memory
+    if (ops) {
+        // clk, op bits, chiplet flag and stack depth from the operation list, on the device (trace/expand.cuh)
+        EZK_CUDA(cudaMemcpyAsync(d_codes, ops->codes, ops->count, cudaMemcpyHostToDevice, stream_));
+        h2d(d_small + 3072, ops->last_row, kWidth * 16);
+        expand_op_columns(stream_, d_codes, ops->count, n, pub.lwe_k + 1, d_small + 3072, d_scan, d_trace_in, d_flag_);
+    }
     {
         NttScale sc{};
         put(sc.cvec[0], inverse(Fp::from_u64(n)));
@@ -453,7 +465,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
                     const uint32_t c = j * G + me;
                     if (c >= kWidth) break;
                     own++;
-                    if (host_columns) {
+                    if (host_columns && uploaded(c)) {
                         if (staged)
                             staged_copy_column(d_trace_in + (size_t)c * n, host_columns[c], n * 16, chunk);
                         else
@@ -490,14 +502,15 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
             uint64_t chunk = 0;
             for (uint32_t g = 0; !staged && g < kWidth / kGroup; g++) {
                 for (uint32_t c = g * kGroup; c < (g + 1) * kGroup; c++)
-                    EZK_CUDA(cudaMemcpyAsync(d_trace_in + (size_t)c * n, host_columns[c], n * 16, cudaMemcpyHostToDevice,
-                                             copy_stream_));
+                    if (uploaded(c))
+                        EZK_CUDA(cudaMemcpyAsync(d_trace_in + (size_t)c * n, host_columns[c], n * 16, cudaMemcpyHostToDevice,
+                                                 copy_stream_));
                 EZK_CUDA(cudaEventRecord(copy_ev_[g], copy_stream_));
             }
             for (uint32_t g = 0; g < kWidth / kGroup; g++) {
                 if (staged) {  // this thread feeds the ring, so the transforms of a group are queued as soon as it is sent
                     for (uint32_t c = g * kGroup; c < (g + 1) * kGroup; c++)
-                        staged_copy_column(d_trace_in + (size_t)c * n, host_columns[c], n * 16, chunk);
+                        if (uploaded(c)) staged_copy_column(d_trace_in + (size_t)c * n, host_columns[c], n * 16, chunk);
                     EZK_CUDA(cudaEventRecord(copy_ev_[g], copy_stream_));
                 }
                 EZK_CUDA(cudaStreamWaitEvent(stream_, copy_ev_[g], 0));
@@ -652,6 +665,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
             check_all_zero(stream_, d_ccoef + 7 * n, n, d_flag_);
             d2h(&flag, d_flag_, sizeof(flag));
         }
+        if (flag & 4) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "the operation list contains an unknown opcode"};
         if (flag & 2)
             throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "the trace contains non-canonical field elements (values >= the modulus)"};
         if (flag)
@@ -886,8 +900,8 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         std::vector<uint64_t> dig_top;                     // per digest: index into tree->top when dig_owner < 0
         size_t idx_off, ndig, out_off;  // offsets into the index array / the gather buffer (16-byte units)
     };
-    std::vector<Opening> ops;
-    ops.reserve(2 + nlayers);
+    std::vector<Opening> openings;
+    openings.reserve(2 + nlayers);
     std::vector<uint64_t> flat;
     size_t out_units = 0;
     // rows_mode 0: whole table on this rank; 1: row p is owned by rank p mod G and sits at index p / G there (packed)
@@ -914,7 +928,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
             }
         op.ndig = op.dig_owner.size();
         out_units += pos.size() * width + 2 * op.ndig;
-        ops.push_back(std::move(op));
+        openings.push_back(std::move(op));
     };
     plan_opening(d_tlde, L_local, kWidth, &trace_tree, sharded ? 1 : 0, positions);
     plan_opening(d_clde, L_local, kCompCols, &comp_tree, sharded ? 1 : 0, positions);
@@ -930,7 +944,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     if (flat.size() > 16384 || out_units > 32768 || out_units * 16 * (exchange ? G : 1) > pinned_bytes_)
         throw ProveFailure{EZK_ERR_INTERNAL, "query staging too small"};
     h2d(d_idx, flat.data(), flat.size() * 8);
-    for (auto& op : ops) {
+    for (auto& op : openings) {
         const uint32_t nq = (uint32_t)op.pos.size();
         gather_rows(stream_, op.table, op.pitch, op.width, d_idx + op.idx_off, nq, d_gather + op.out_off);
         if (op.ndig)
@@ -966,8 +980,8 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         w.u32((uint32_t)paths.size());
         w.bytes(paths.data(), paths.size());
     };
-    write_opening(ops[0]);
-    write_opening(ops[1]);
+    write_opening(openings[0]);
+    write_opening(openings[1]);
     // OodFrame
     w.u16((uint16_t)(1 + ood_wire.size() * 16));
     w.u8(2);
@@ -977,7 +991,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     for (Fp v : ood_comp) w.element(v);
     // FriProof
     w.u8((uint8_t)nlayers);
-    for (size_t k = 2; k < ops.size(); k++) write_opening(ops[k]);
+    for (size_t k = 2; k < openings.size(); k++) write_opening(openings[k]);
     w.u16((uint16_t)(remainder.size() * 16));
     for (Fp v : remainder) w.element(v);
     w.u8(1);

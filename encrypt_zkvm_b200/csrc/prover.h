@@ -22,6 +22,14 @@ struct PublicInputs {
     uint32_t lwe_k = 4, lwe_delta = 16;
 };
 
+// Executed operation list of the program (one code byte per operation, vm/src/processor/opcodes.rs:30-43) and the
+// random last row: enough to build 8 of the 28 trace columns on the device (csrc/trace/expand.cuh).
+struct OpList {
+    const uint8_t* codes = nullptr;
+    uint64_t count = 0;
+    const uint8_t* last_row = nullptr;  // 28 x 16 bytes
+};
+
 class GpuProver {
 public:
     explicit GpuProver(int device);
@@ -29,8 +37,9 @@ public:
     GpuProver(const GpuProver&) = delete;
 
     // host columns (28 pointers) or device-resident trace; exactly one of them non-null
+    // ops (host columns only): the columns of kOpColumns are generated on the device and their pointers are ignored
     std::vector<uint8_t> prove(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
-                               const PublicInputs& pub, const ProofOptions& opt);
+                               const PublicInputs& pub, const ProofOptions& opt, const OpList* ops = nullptr);
 
     // Multi-GPU single proof: after join(), prove() must be called by every rank of the group with the
     // same trace, public inputs and options; each rank extends / evaluates / hashes the LDE cosets it owns, the
@@ -62,7 +71,7 @@ public:
 
 private:
     std::vector<uint8_t> prove_impl(const uint8_t* const* host_columns, const uint4* device_trace, uint64_t n,
-                                    const PublicInputs& pub, const ProofOptions& opt);
+                                    const PublicInputs& pub, const ProofOptions& opt, const OpList* ops);
     struct Arena {
         uint4* base = nullptr;
         size_t capacity = 0, used = 0;  // in 16-byte units

@@ -179,6 +179,24 @@ class ExecutionProver:
         rc = lib.ezk_prover_prove(self._handle, C.byref(t), C.byref(pi), C.byref(opt), C.byref(out), C.byref(out_len))
         return self._finish(rc, out, out_len)
 
+    OP_COLUMNS = (0, 1, 2, 3, 4, 5, 6, 11)  # clk, op bits, chiplet flag, stack depth: built on the device from the op list
+
+    def prove_with_ops(self, trace, op_codes, last_row=None) -> Proof:
+        """`prove` with the eight bookkeeping columns generated on the device from the executed operation codes
+        (`Program.ops()[0]`): the corresponding rows of `trace` are never read.  last_row defaults to trace[:, n-1]."""
+        a = _as_trace_array(trace)
+        n = a.shape[1]
+        codes = np.ascontiguousarray(op_codes, dtype=np.uint8)
+        last = np.ascontiguousarray(a[:, n - 1] if last_row is None else last_row, dtype=np.uint64).reshape(TRACE_WIDTH, 2)
+        cols = (C.c_void_p * TRACE_WIDTH)(*[None if c in self.OP_COLUMNS else a[c].ctypes.data for c in range(TRACE_WIDTH)])
+        t = EzkTrace(C.cast(cols, C.POINTER(C.c_void_p)), TRACE_WIDTH, n)
+        ops = _lib.EzkOpList(codes.ctypes.data, len(codes), last.ctypes.data)
+        pi, opt = self.pub_inputs.to_c(), self.options.to_c()
+        out, out_len = C.c_void_p(), C.c_size_t()
+        rc = lib.ezk_prover_prove_ops(self._handle, C.byref(t), C.byref(ops), C.byref(pi), C.byref(opt), C.byref(out),
+                                      C.byref(out_len))
+        return self._finish(rc, out, out_len)
+
     def prove_device(self, device_ptr: int, n: int) -> Proof:
         """Same with the trace already in device memory (28 contiguous columns of n elements)."""
         pi, opt = self.pub_inputs.to_c(), self.options.to_c()

@@ -66,6 +66,14 @@ class Program:
         lib.ezk_program_ops(self._handle, codes, values)
         return list(zip(codes, values))
 
+    def op_codes(self) -> np.ndarray:
+        """The executed operation codes (compiler padding included) as a uint8 array: the input of
+        `ExecutionProver.prove_with_ops` (device-side generation of the clk / decoder / flag / depth columns)."""
+        n = len(self)
+        codes = np.empty(n, dtype=np.uint8)
+        lib.ezk_program_ops(self._handle, codes.ctypes.data_as(C.POINTER(C.c_uint8)), None)
+        return codes
+
     def hash(self) -> List[int]:
         buf = C.create_string_buffer(32)
         lib.ezk_program_hash(self._handle, buf)

@@ -113,6 +113,22 @@ int ezk_prover_prove_device(ezk_prover* p, const void* d_trace, uint64_t length,
 int ezk_prove(const ezk_trace* trace, const ezk_public_inputs* pub, const ezk_options* opt, uint8_t** proof,
               size_t* proof_len);
 
+/* The same proof from a trace whose "bookkeeping" columns are built on the device (scoped to what is
+ * parallel): clk (column 0), the five op bits (1..5), the chiplet flag (6) and the stack depth (11) are pure functions
+ * of the executed operation list - one code byte per operation (vm/src/processor/opcodes.rs:30-43, in execution order,
+ * the compiler's padding NOOPs included: `Program::get_code()`) - so a caller may pass NULL for those eight column
+ * pointers and the list instead: 8 x 16 bytes per row less to upload.  The Rescue sponge columns (7..10) and the
+ * stack registers (12..27) still come from the host VM (vm/src/processor/chiplets.rs:92-112, stack.rs:48-70).
+ * last_row: the 28 values of row length-1 (the reference's thread_rng row, vm/src/processor/mod.rs:86-92).
+ * Returns the bytes ezk_prover_prove returns for the full trace. */
+typedef struct ezk_op_list {
+    const uint8_t* codes;          /* count operation codes */
+    uint64_t count;                /* executed operations, < trace length */
+    const uint8_t (*last_row)[16]; /* 28 elements */
+} ezk_op_list;
+int ezk_prover_prove_ops(ezk_prover* p, const ezk_trace* trace, const ezk_op_list* ops, const ezk_public_inputs* public_inputs,
+                         const ezk_options* options, uint8_t** proof, size_t* proof_len);
+
 /* winterfell::verify::<ProcessorAir, Blake3_256, DefaultRandomCoin<Blake3_256>>(proof, pub_inputs,
  * &AcceptableOptions::MinConjecturedSecurity(min_conjectured_security)) as called at vm/src/lib.rs:91-98 and
  * examples/linear_regression/src/main.rs:81-85.  Returns EZK_OK when the proof is accepted and

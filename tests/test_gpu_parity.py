@@ -413,3 +413,31 @@ def test_product_verifier_on_a_2p18_proof_and_other_options(gpu_prover_factory):
     with ezk.ExecutionProver(opt, case.program_hash, case.outputs, ezk.ServerKey()) as p:  # delta 16: wrong AIR parameter
         with pytest.raises(ezk.VerifierError):
             p.verify(proof, min_conjectured_security=59)
+
+
+@pytest.mark.parametrize("which", ["lr", "small", (1, 10), (2, 12), (3, 14)])
+def test_bookkeeping_columns_generated_on_the_device(gpu_prover_factory, which):
+    """SURVEY 8f-2 (scoped): clk, op bits, chiplet flag and stack depth come from the operation list on the device;
+    the proof must equal the one from the host VM's full trace, byte for byte, and the eight host columns are never read
+    (they are poisoned here).  Reference layout of those columns: vm/src/processor/{system,decoder,chiplets,stack}.rs."""
+    ezk = gpu_prover_factory
+    case = lr_case() if which == "lr" else small_case() if which == "small" else synthetic(*which)
+    codes = case.program.op_codes()
+    n = case.trace.shape[1]
+    assert len(codes) < n
+    poisoned = case.trace.copy()
+    for c in ezk.ExecutionProver.OP_COLUMNS:
+        poisoned[c] = 0xFFFFFFFFFFFFFFFF
+    with ezk.ExecutionProver(ezk.ProofOptions(), case.program_hash, case.outputs, case.key) as p:
+        want = p.prove(case.trace).to_bytes()
+        got = p.prove_with_ops(poisoned, codes, last_row=case.trace[:, n - 1]).to_bytes()
+        assert got == want
+        with pytest.raises(ezk.ProverError):  # an unknown opcode is rejected, not proved
+            bad = codes.copy()
+            bad[3] = 0b11111
+            p.prove_with_ops(poisoned, bad, last_row=case.trace[:, n - 1])
+        with pytest.raises(ezk.ProverError):  # a wrong operation makes the trace violate the AIR
+            bad = codes.copy()
+            bad[0] = 0b10000 if codes[0] != 0b10000 else 0b10001
+            p.prove_with_ops(poisoned, bad, last_row=case.trace[:, n - 1])
+        assert p.prove_with_ops(poisoned, codes, last_row=case.trace[:, n - 1]).to_bytes() == want
