@@ -3,6 +3,7 @@
 #include "../../include/ezkvm_prover.h"
 #include "common.h"
 #include "host/vm.h"
+#include "dist/shard_layout.h"
 #include "prover.h"
 #include "trace/expand.cuh"
 #include <algorithm>
@@ -130,6 +131,64 @@ int ezk_selftest_host_field(const void* a, const void* b, size_t n, void* out4n)
         }
     });
 }
+// Host-only model of the sharded Merkle commitment: leaf digests spread over G ranks by row ownership, routed with the
+// all-to-all rule of dist/shard_layout.h, subtrees + host-side top, then every node looked up through shard_node_home
+// and every batch-proof node list checked against the unsplit tree.
+int ezk_selftest_shard_layout(uint32_t world, uint32_t log_leaves, uint64_t seed) {
+    return guarded([&] {
+        const uint32_t G = world, glog = G == 8 ? 3 : G == 4 ? 2 : G == 2 ? 1 : 0;
+        if ((1u << glog) != G || log_leaves < 2 * glog + 1 || log_leaves > 20) throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad shape"};
+        const uint64_t leaves = 1ull << log_leaves, ll = leaves >> glog, chunk = ll >> glog;
+        SplitMix64 rng(seed);
+        std::vector<Hash32> leaf(leaves);
+        for (auto& h : leaf)
+            for (int i = 0; i < 4; i++) {
+                const uint64_t v = rng.next();
+                memcpy(h.data() + 8 * i, &v, 8);
+            }
+        // the unsplit tree
+        std::vector<Hash32> full(2 * leaves);
+        for (uint64_t i = 0; i < leaves; i++) full[leaves + i] = leaf[i];
+        for (uint64_t k = leaves - 1; k >= 1; k--) full[k] = merge_digests(full[2 * k], full[2 * k + 1]);
+        // packed digests of every rank, the all-to-all, the unpacking
+        std::vector<std::vector<Hash32>> packed(G, std::vector<Hash32>(ll)), sub(G, std::vector<Hash32>(2 * ll));
+        for (uint32_t r = 0; r < G; r++)
+            for (uint64_t t = 0; t < ll; t++) packed[r][t] = leaf[(uint64_t)G * t + r];
+        for (uint32_t src = 0; src < G; src++)
+            for (uint64_t t = 0; t < ll; t++) {
+                const uint32_t dst = shard_leaf_destination(leaves, glog, t);
+                const uint64_t local = shard_local_leaf(G, src, t % chunk);
+                if (dst >= G || local >= ll) throw ProveFailure{EZK_ERR_INTERNAL, "routing out of range"};
+                sub[dst][ll + local] = packed[src][t];
+            }
+        for (uint32_t q = 0; q < G; q++) {
+            for (uint64_t u = 0; u < ll; u++)
+                if (sub[q][ll + u] != leaf[(uint64_t)q * ll + u]) throw ProveFailure{EZK_ERR_INTERNAL, "a leaf digest reached the wrong subtree slot"};
+            for (uint64_t k = ll - 1; k >= 1; k--) sub[q][k] = merge_digests(sub[q][2 * k], sub[q][2 * k + 1]);
+        }
+        std::vector<Hash32> top(2 * G);
+        for (uint32_t q = 0; q < G; q++) top[G + q] = sub[q][1];
+        for (uint32_t k = G - 1; k >= 1; k--) top[k] = merge_digests(top[2 * k], top[2 * k + 1]);
+        if (top[1] != full[1]) throw ProveFailure{EZK_ERR_INTERNAL, "root of the split tree differs"};
+        auto fetch = [&](uint64_t k) {
+            const NodeHome h = shard_node_home(G, glog, k);
+            return h.owner < 0 ? top[h.index] : sub[h.owner][h.index];
+        };
+        for (uint64_t k = 1; k < 2 * leaves; k++)
+            if (fetch(k) != full[k]) throw ProveFailure{EZK_ERR_INTERNAL, "node lookup through shard_node_home differs"};
+        // authentication paths of random query sets
+        for (int round = 0; round < 8; round++) {
+            std::vector<uint64_t> pos;
+            for (int q = 0; q < 32; q++) pos.push_back(rng.next() & (leaves - 1));
+            std::sort(pos.begin(), pos.end());
+            pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+            for (auto& list : batch_proof_node_indices(leaves, pos))
+                for (uint64_t k : list)
+                    if (fetch(k) != full[k]) throw ProveFailure{EZK_ERR_INTERNAL, "authentication path node differs"};
+        }
+    });
+}
+
 void ezk_default_options(ezk_options* out) {
     if (!out) return;
     out->num_queries = 32, out->blowup_factor = 8, out->grinding_factor = 0, out->field_extension = 1;

@@ -7,6 +7,7 @@
 #include "../../include/ezkvm_rescue_constants.h"
 #include "common.h"
 #include "compose/compose.cuh"
+#include "dist/shard_layout.h"
 #include "fri/fri.cuh"
 #include "host/air_host.h"
 #include "merkle/merkle.cuh"
@@ -23,11 +24,6 @@ std::atomic<uint64_t> g_launches{0};
 
 constexpr uint32_t kWidth = 28, kCompCols = 7, kTransitions = 20, kAssertions = 22, kCycle = 16, kPeriodic = 9;
 
-inline unsigned ilog2_floor(uint64_t v) {
-    unsigned k = 0;
-    while (v >>= 1) k++;
-    return k;
-}
 inline void put(uint64_t dst[2], Fp v) {
     dst[0] = (uint64_t)v.v;
     dst[1] = (uint64_t)(v.v >> 64);
@@ -917,13 +913,10 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
             for (uint64_t k : v) {
                 if (!tree->split) {
                     op.dig_owner.push_back((int32_t)me), op.dig_top.push_back(0), flat.push_back(k);
-                } else if (k < 2ull * G) {
-                    op.dig_owner.push_back(-1), op.dig_top.push_back(k), flat.push_back(1);
                 } else {
-                    const unsigned d = ilog2_floor(k) - glog;  // depth below the subtree roots
-                    const uint32_t owner = (uint32_t)((k >> d) - G);
-                    op.dig_owner.push_back((int32_t)owner), op.dig_top.push_back(0);
-                    flat.push_back(owner == me ? ((1ull << d) | (k & ((1ull << d) - 1))) : 1);
+                    const NodeHome home = shard_node_home(G, glog, k);  // subtree of a rank, or the host-side top levels
+                    op.dig_owner.push_back(home.owner), op.dig_top.push_back(home.owner < 0 ? home.index : 0);
+                    flat.push_back(home.owner == (int)me ? home.index : 1);
                 }
             }
         op.ndig = op.dig_owner.size();

@@ -91,6 +91,12 @@ void ezk_set_wire_compat(const ezk_wire_compat* in); /* NULL restores the defaul
  * Needs no GPU.  Returns EZK_OK or EZK_ERR_INTERNAL. */
 int ezk_selftest_copy_pool(uint32_t threads, size_t bytes);
 
+/* Host-side self-test of the index arithmetic of the sharded proof (csrc/dist/shard_layout.h): models the leaf-digest
+ * all-to-all, the per-rank subtrees and the host-side top levels of a split Merkle commitment with `world` ranks and
+ * 2^log_leaves leaves, and checks root, every node lookup and random authentication paths against the unsplit tree.
+ * Needs no GPU.  Returns EZK_OK or EZK_ERR_INTERNAL. */
+int ezk_selftest_shard_layout(uint32_t world, uint32_t log_leaves, uint64_t seed);
+
 /* Host-side self-test of the f128 arithmetic behind the transcript and the VM: for n pairs (a_i, b_i) of canonical
  * elements writes a_i * b_i (portable product), a_i * b_i (the product the Rescue sponge uses), a_i^2 and
  * a_i^INV_ALPHA (the sponge's addition chain) - 4 * n elements - for the caller to compare with big integers.

@@ -72,3 +72,14 @@ def test_two_ranks_over_gloo():
     assert by_rank[0][3] == pytest.approx(by_rank[1][3])      # MAX over ranks, same on both
     assert by_rank[0][3] >= 0.1                               # at least rank 1's two sleeps
     assert by_rank[0][5] == pytest.approx(num_units / by_rank[0][3])
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_shard_layout_of_the_split_merkle_commitment(world):
+    """Index arithmetic of the sharded proof on the CPU (csrc/dist/shard_layout.h, shared with the prover's opening
+    planner): leaf-digest all-to-all, per-rank subtrees, host-side top levels, node lookup and authentication paths
+    agree with the unsplit tree for every supported world size."""
+    from encrypt_zkvm_b200 import _lib
+    for log_leaves in (7, 10, 13):
+        assert _lib.lib.ezk_selftest_shard_layout(world, log_leaves, 1234 + log_leaves) == 0, _lib.lib.ezk_last_error()
+    assert _lib.lib.ezk_selftest_shard_layout(3, 10, 1) != 0  # not a supported world size
