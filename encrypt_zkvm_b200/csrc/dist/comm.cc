@@ -106,6 +106,18 @@ void LocalGroup::exchange(int rank, const void* send, void* recv, size_t bytes, 
     barrier();  // nobody reuses its send buffer before every member has read it
 }
 
+void LocalGroup::send_recv(int rank, const void* send, void* recv, int src, size_t bytes, cudaStream_t s) {
+    EZK_CUDA(cudaStreamSynchronize(s));
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        slots_[rank] = send;
+    }
+    barrier();
+    EZK_CUDA(cudaMemcpyAsync(recv, slots_[src], bytes, cudaMemcpyDefault, s));
+    EZK_CUDA(cudaStreamSynchronize(s));
+    barrier();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 
 void Comm::reset() {
@@ -165,6 +177,22 @@ void Comm::all_gather(const void* send, void* recv, size_t bytes, cudaStream_t s
         return;
     }
     check(api().AllGather(send, recv, bytes, ncclUint8, static_cast<ncclComm_t>(comm_), s), "ncclAllGather");
+}
+
+void Comm::send_recv(const void* send, int dst, void* recv, int src, size_t bytes, cudaStream_t s) const {
+    if (world_ == 1) {
+        if (send != recv) EZK_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, s));
+        return;
+    }
+    if (local_) {
+        local_->send_recv(rank_, send, recv, src, bytes, s);
+        return;
+    }
+    ncclComm_t c = static_cast<ncclComm_t>(comm_);
+    check(api().GroupStart(), "ncclGroupStart");
+    check(api().Send(send, bytes, ncclUint8, dst, c, s), "ncclSend");
+    check(api().Recv(recv, bytes, ncclUint8, src, c, s), "ncclRecv");
+    check(api().GroupEnd(), "ncclGroupEnd");
 }
 
 void Comm::all_to_all(const void* send, void* recv, size_t bytes, cudaStream_t s) const {

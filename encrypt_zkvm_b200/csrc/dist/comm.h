@@ -24,6 +24,8 @@ public:
     int world() const { return world_; }
     // recv[q * bytes ..) = (all-gather) peer q's send[0 .. bytes) / (all-to-all) peer q's send[rank * bytes ..)
     void exchange(int rank, const void* send, void* recv, size_t bytes, bool all_to_all, cudaStream_t s);
+    // recv[0 .. bytes) = peer src's send[0 .. bytes); every member calls it in the same step (ring-shifted pairs)
+    void send_recv(int rank, const void* send, void* recv, int src, size_t bytes, cudaStream_t s);
     // a member that fails wakes the others instead of leaving them in the barrier
     void abort();
 
@@ -56,6 +58,9 @@ public:
     void all_gather(const void* send, void* recv, size_t bytes, cudaStream_t s) const;
     // recv[q * bytes .. (q+1) * bytes) = rank q's send[rank * bytes .. (rank+1) * bytes)
     void all_to_all(const void* send, void* recv, size_t bytes, cudaStream_t s) const;
+    // one step of a ring-shifted exchange: send[0 .. bytes) goes to rank dst, recv[0 .. bytes) comes from rank src; all
+    // ranks call it with dst = rank + k, src = rank - k (mod world) for the same k
+    void send_recv(const void* send, int dst, void* recv, int src, size_t bytes, cudaStream_t s) const;
     // called when a proof fails on this rank: in-process peers are released from their barriers
     void abort() const;
 

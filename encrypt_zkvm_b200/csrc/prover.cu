@@ -396,11 +396,32 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
             return root;
         }
         const uint64_t ll = leaves >> glog;  // leaves of this rank's subtree
-        if (table) hash_rows_sharded(stream_, table, ll, width, ll, sh, d_pack);
         // rank r's packed digests are those of rows r, r + G, ...: chunk q of them lies in rank q's leaf range
         tree.split = true, tree.leaves_local = ll, tree.nodes = alloc(4 * ll);
-        comm_.all_to_all(d_pack, d_recv, (ll >> glog) * 32, stream_);
-        count_launch();
+        const uint64_t chunk = ll >> glog;  // rows per destination
+        if (table && G > 1) {
+            // hash and exchange pipelined by destination, ring-shifted so that every step pairs each rank with one
+            // sender and one receiver: while the digests for rank me + k travel (auxiliary stream), the rows for rank
+            // me + k + 1 are being hashed; the own chunk comes last and needs no transfer
+            EZK_CUDA(cudaEventRecord(share_ev_[60], stream_));
+            EZK_CUDA(cudaStreamWaitEvent(aux_stream_, share_ev_[60], 0));  // d_recv / d_pack are free
+            for (uint32_t k = 1; k <= G; k++) {
+                const uint32_t dst = (me + k) % G, src = (me + G - k % G) % G;
+                uint4* out = k == G ? d_recv + 2 * (size_t)me * chunk : d_pack + 2 * (size_t)dst * chunk;
+                hash_rows_sharded(stream_, table + (size_t)dst * chunk, ll, width, chunk, sh, out);
+                if (k == G) break;
+                EZK_CUDA(cudaEventRecord(share_ev_[40 + k], stream_));
+                EZK_CUDA(cudaStreamWaitEvent(aux_stream_, share_ev_[40 + k], 0));
+                comm_.send_recv(out, (int)dst, d_recv + 2 * (size_t)src * chunk, (int)src, chunk * 32, aux_stream_);
+                count_launch();
+            }
+            EZK_CUDA(cudaEventRecord(share_ev_[61], aux_stream_));
+            EZK_CUDA(cudaStreamWaitEvent(stream_, share_ev_[61], 0));
+        } else {
+            if (table) hash_rows_sharded(stream_, table, ll, width, ll, sh, d_pack);
+            comm_.all_to_all(d_pack, d_recv, chunk * 32, stream_);
+            count_launch();
+        }
         unpack_rows(stream_, d_recv, ll >> glog, glog, 2, tree.nodes + 2 * ll);
         merkle_build(stream_, tree.nodes, ll);
         uint4* d_roots = d_small + 1024;
@@ -452,8 +473,54 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
                 const uint32_t cols = std::min<uint32_t>((j1 - j0) * G, kWidth - (uint32_t)c0);
                 lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L_local, L_local, d_tmp, cols, log_n, cs);
             };
+            if (device_trace) {
+                // resident trace: interpolate all own columns at once, start every all-gather, and extend the OWN
+                // columns first - they need no exchange, so the first all-gathers travel under useful work; then the
+                // columns of the other ranks, batch by batch as they arrive
+                const uint32_t mine = (kWidth - me + G - 1) / G;
+                mark(), mark_pending = false;
+                for (uint32_t k = 0; k < mine; k++) check_canonical(stream_, own_src + (size_t)(k * G + me) * n, n, d_flag_);
+                ntt_columns(tables_, stream_, own_src + (size_t)me * n, (uint64_t)G * n, d_tcoef + (size_t)me * n, (uint64_t)G * n, d_tmp,
+                            mine, log_n, true, &sc);
+                EZK_CUDA(cudaEventRecord(share_ev_[0], stream_));
+                EZK_CUDA(cudaStreamWaitEvent(aux_stream_, share_ev_[0], 0));
+                for (uint32_t j = 0; j < rounds; j++) {
+                    comm_.all_gather(d_tcoef + (size_t)(j * G + me) * n, d_tcoef + (size_t)j * G * n, n * 16, aux_stream_);
+                    count_launch();
+                    EZK_CUDA(cudaEventRecord(share_ev_[2 * j + 1], aux_stream_));
+                }
+                // columns c0, c0 + step, ... (count of them) in one launch, at most 8 at a time (scratch)
+                auto extend_progression = [&](uint32_t c0, uint32_t step, uint32_t count) {
+                    for (uint32_t k = 0; k < count; k += 8)
+                        lde_columns(tables_, stream_, d_tcoef + (size_t)(c0 + k * step) * n, (uint64_t)step * n,
+                                    d_tlde + (size_t)(c0 + k * step) * L_local, (uint64_t)step * L_local, d_tmp, std::min(8u, count - k),
+                                    log_n, cs);
+                };
+                extend_progression(me, G, mine);
+                for (uint32_t j0 = 0; j0 < rounds; j0 += rb) {
+                    const uint32_t j1 = std::min(rounds, j0 + rb);
+                    EZK_CUDA(cudaStreamWaitEvent(stream_, share_ev_[2 * (j1 - 1) + 1], 0));
+                    if (G - 1 <= 2 * (j1 - j0)) {
+                        // one launch per foreign rank q: its columns j G + q of the batch
+                        for (uint32_t q = 0; q < G; q++) {
+                            if (q == me) continue;
+                            uint32_t count = 0;
+                            while (j0 + count < j1 && (j0 + count) * G + q < kWidth) count++;
+                            if (count) extend_progression(j0 * G + q, G, count);
+                        }
+                    } else {
+                        // per round the two contiguous ranges on either side of the own column
+                        for (uint32_t j = j0; j < j1; j++) {
+                            const uint32_t lo = j * G, hi = std::min(kWidth, lo + G), own = lo + me;
+                            if (own > lo) extend_progression(lo, 1, std::min(own, hi) - lo);
+                            if (own + 1 < hi) extend_progression(own + 1, 1, hi - own - 1);
+                        }
+                    }
+                }
+            } else
             // software pipeline on the compute stream: interpolate(b), extend(b - 1), interpolate(b + 1), ... so that the
             // all-gather of batch b (auxiliary stream) and the upload of batch b + 1 run under the extension of batch b - 1
+            {
             for (uint32_t j0 = 0; j0 < rounds; j0 += rb) {
                 const uint32_t j1 = std::min(rounds, j0 + rb);
                 uint32_t own = 0;  // own columns of this batch: c = (j0 + k) G + me < 28
@@ -488,6 +555,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
                 if (j0 >= rb) extend_batch(j0 - rb);
             }
             extend_batch(((rounds - 1) / rb) * rb);
+            }
         } else if (host_columns) {
             // Upload and transform in column groups: the copy of group k+1 (copy stream) overlaps the
             // interpolation + LDE of group k (compute stream).  Columns are independent until the row hash.

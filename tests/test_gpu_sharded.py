@@ -61,10 +61,12 @@ def test_a_rank_reads_only_the_columns_it_owns(gpu_prover_factory):
     got = ezk.prove_sharded_in_process(4, ezk.ProofOptions(), case.program_hash, case.outputs, case.key, case.trace,
                                        own_columns_only=True)
     assert all(g == want for g in got)
+    # device-resident traces take their own schedule (own columns extended first, foreign columns as they arrive)
     dev = torch.from_numpy(case.trace.view(np.int64)).cuda()
-    got = ezk.prove_sharded_in_process(2, ezk.ProofOptions(), case.program_hash, case.outputs, case.key, case.trace,
-                                       device_ptr=dev.data_ptr())
-    assert all(g == want for g in got)
+    for world in (2, 4, 8):
+        got = ezk.prove_sharded_in_process(world, ezk.ProofOptions(), case.program_hash, case.outputs, case.key, case.trace,
+                                           device_ptr=dev.data_ptr())
+        assert all(g == want for g in got), world
 
 
 def test_other_options_and_verifier(gpu_prover_factory, oracle):
