@@ -90,6 +90,16 @@ void LocalGroup::barrier() {
     }
 }
 
+void LocalGroup::publish(int rank, void* ptr, void* all[8]) {
+    {
+        std::lock_guard<std::mutex> lock(mu_);
+        slots_[rank] = ptr;
+    }
+    barrier();
+    for (int q = 0; q < world_; q++) all[q] = const_cast<void*>(slots_[q]);
+    barrier();
+}
+
 void LocalGroup::exchange(int rank, const void* send, void* recv, size_t bytes, bool all_to_all, cudaStream_t s) {
     EZK_CUDA(cudaStreamSynchronize(s));  // this member's data is complete
     {
@@ -106,21 +116,125 @@ void LocalGroup::exchange(int rank, const void* send, void* recv, size_t bytes, 
     barrier();  // nobody reuses its send buffer before every member has read it
 }
 
-void LocalGroup::send_recv(int rank, const void* send, void* recv, int src, size_t bytes, cudaStream_t s) {
-    EZK_CUDA(cudaStreamSynchronize(s));
-    {
-        std::lock_guard<std::mutex> lock(mu_);
-        slots_[rank] = send;
-    }
-    barrier();
-    EZK_CUDA(cudaMemcpyAsync(recv, slots_[src], bytes, cudaMemcpyDefault, s));
-    EZK_CUDA(cudaStreamSynchronize(s));
-    barrier();
-}
-
 // ---------------------------------------------------------------------------------------------------------
 
+void Comm::close_peers() {
+    for (int q = 0; q < 8; q++) {
+        if (peer_opened_[q] && peer_base_[q]) cudaIpcCloseMemHandle(peer_base_[q]);
+        peer_base_[q] = nullptr, peer_gen_[q] = 0, peer_opened_[q] = false;
+    }
+    peers_ok_ = false, own_base_ = nullptr;
+}
+
+namespace {
+struct PeerRecord {  // what every rank publishes about its workspace
+    cudaIpcMemHandle_t handle;
+    uint64_t generation;
+    uint64_t bytes;
+    uint32_t ok;  // second round: all mappings of this rank are in place
+    uint32_t pad;
+};
+}  // namespace
+
+bool Comm::map_peers(void* base, size_t bytes, uint64_t generation, void* pinned, void* scratch, cudaStream_t s) {
+    if (world_ == 1) return false;
+    own_base_ = base;
+    if (local_) {
+        // members of one process: plain pointers (peer access between their devices is enabled on demand)
+        void* all[8];
+        local_->publish(rank_, base, all);
+        int dev = 0, ok = 1;
+        EZK_CUDA(cudaGetDevice(&dev));
+        for (int q = 0; q < world_; q++) {
+            peer_base_[q] = all[q], peer_opened_[q] = false;
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, all[q]) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+            } else if (attr.device != dev) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                cudaGetLastError();
+            }
+        }
+        void* oks[8];
+        local_->publish(rank_, ok ? base : nullptr, oks);
+        peers_ok_ = true;
+        for (int q = 0; q < world_; q++) peers_ok_ = peers_ok_ && oks[q] != nullptr;
+        return peers_ok_;
+    }
+    static_assert(sizeof(PeerRecord) == 88, "PeerRecord layout");
+    PeerRecord* host = static_cast<PeerRecord*>(pinned);
+    PeerRecord* dev = static_cast<PeerRecord*>(scratch);
+    auto gather = [&](const PeerRecord& mine, PeerRecord out[8]) {
+        host[0] = mine;
+        EZK_CUDA(cudaMemcpyAsync(dev, host, sizeof(PeerRecord), cudaMemcpyHostToDevice, s));
+        check(api().AllGather(dev, dev + 1, sizeof(PeerRecord), ncclUint8, static_cast<ncclComm_t>(comm_), s), "ncclAllGather");
+        EZK_CUDA(cudaMemcpyAsync(host + 1, dev + 1, sizeof(PeerRecord) * world_, cudaMemcpyDeviceToHost, s));
+        EZK_CUDA(cudaStreamSynchronize(s));
+        memcpy(out, host + 1, sizeof(PeerRecord) * world_);
+    };
+    PeerRecord mine{};
+    if (cudaIpcGetMemHandle(&mine.handle, base) != cudaSuccess) {
+        cudaGetLastError();
+        memset(&mine.handle, 0, sizeof(mine.handle));
+        mine.generation = 0;  // 0 = no handle: every rank falls back
+    } else {
+        mine.generation = generation ? generation : 1;
+    }
+    mine.bytes = bytes;
+    PeerRecord all[8];
+    gather(mine, all);
+    bool changed = false, possible = true;
+    for (int q = 0; q < world_; q++) {
+        possible = possible && all[q].generation != 0;
+        changed = changed || all[q].generation != peer_gen_[q];
+    }
+    if (!possible) {
+        close_peers();
+        own_base_ = base;
+        return false;
+    }
+    if (!changed) return peers_ok_;
+    uint32_t ok = 1;
+    for (int q = 0; q < world_; q++) {
+        if (all[q].generation == peer_gen_[q]) continue;
+        if (peer_opened_[q] && peer_base_[q]) cudaIpcCloseMemHandle(peer_base_[q]);
+        peer_base_[q] = nullptr, peer_opened_[q] = false, peer_gen_[q] = 0;
+        if (q == rank_) {
+            peer_base_[q] = base, peer_gen_[q] = all[q].generation;
+            continue;
+        }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+            continue;
+        }
+        peer_base_[q] = p, peer_opened_[q] = true, peer_gen_[q] = all[q].generation;
+    }
+    mine.ok = ok;
+    gather(mine, all);  // the same verdict on every rank
+    peers_ok_ = true;
+    for (int q = 0; q < world_; q++) peers_ok_ = peers_ok_ && all[q].ok != 0;
+    return peers_ok_;
+}
+
+void Comm::barrier(void* scratch, cudaStream_t s) const {
+    if (world_ == 1) return;
+    if (local_) {
+        EZK_CUDA(cudaStreamSynchronize(s));
+        local_->host_barrier();
+        return;
+    }
+    // a 4-byte all-gather on the stream: it completes on a rank only after every rank has reached it, i.e. after the
+    // kernels those ranks queued before it - and their peer stores - are done
+    uint32_t* d = static_cast<uint32_t*>(scratch);
+    check(api().AllGather(d + rank_, d, sizeof(uint32_t), ncclUint8, static_cast<ncclComm_t>(comm_), s), "ncclAllGather");
+}
+
 void Comm::reset() {
+    close_peers();
     if (comm_) {
         api().CommDestroy(static_cast<ncclComm_t>(comm_));
         comm_ = nullptr;
@@ -130,6 +244,7 @@ void Comm::reset() {
 }
 
 Comm::~Comm() {
+    close_peers();
     if (comm_) api().CommDestroy(static_cast<ncclComm_t>(comm_));
 }
 
@@ -177,22 +292,6 @@ void Comm::all_gather(const void* send, void* recv, size_t bytes, cudaStream_t s
         return;
     }
     check(api().AllGather(send, recv, bytes, ncclUint8, static_cast<ncclComm_t>(comm_), s), "ncclAllGather");
-}
-
-void Comm::send_recv(const void* send, int dst, void* recv, int src, size_t bytes, cudaStream_t s) const {
-    if (world_ == 1) {
-        if (send != recv) EZK_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, s));
-        return;
-    }
-    if (local_) {
-        local_->send_recv(rank_, send, recv, src, bytes, s);
-        return;
-    }
-    ncclComm_t c = static_cast<ncclComm_t>(comm_);
-    check(api().GroupStart(), "ncclGroupStart");
-    check(api().Send(send, bytes, ncclUint8, dst, c, s), "ncclSend");
-    check(api().Recv(recv, bytes, ncclUint8, src, c, s), "ncclRecv");
-    check(api().GroupEnd(), "ncclGroupEnd");
 }
 
 void Comm::all_to_all(const void* send, void* recv, size_t bytes, cudaStream_t s) const {

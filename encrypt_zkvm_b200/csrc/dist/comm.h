@@ -24,10 +24,11 @@ public:
     int world() const { return world_; }
     // recv[q * bytes ..) = (all-gather) peer q's send[0 .. bytes) / (all-to-all) peer q's send[rank * bytes ..)
     void exchange(int rank, const void* send, void* recv, size_t bytes, bool all_to_all, cudaStream_t s);
-    // recv[0 .. bytes) = peer src's send[0 .. bytes); every member calls it in the same step (ring-shifted pairs)
-    void send_recv(int rank, const void* send, void* recv, int src, size_t bytes, cudaStream_t s);
     // a member that fails wakes the others instead of leaving them in the barrier
     void abort();
+    // every member publishes a pointer; returns after all have, with all[q] = member q's pointer
+    void publish(int rank, void* ptr, void* all[8]);
+    void host_barrier() { barrier(); }
 
 private:
     void barrier();
@@ -58,14 +59,32 @@ public:
     void all_gather(const void* send, void* recv, size_t bytes, cudaStream_t s) const;
     // recv[q * bytes .. (q+1) * bytes) = rank q's send[rank * bytes .. (rank+1) * bytes)
     void all_to_all(const void* send, void* recv, size_t bytes, cudaStream_t s) const;
-    // one step of a ring-shifted exchange: send[0 .. bytes) goes to rank dst, recv[0 .. bytes) comes from rank src; all
-    // ranks call it with dst = rank + k, src = rank - k (mod world) for the same k
-    void send_recv(const void* send, int dst, void* recv, int src, size_t bytes, cudaStream_t s) const;
     // called when a proof fails on this rank: in-process peers are released from their barriers
     void abort() const;
 
+    // ---- peer memory (NVLink P2P stores fused into kernels) ----
+    // Collective, once per proof: makes the workspaces of all ranks addressable from this one.  `base`/`bytes` = this
+    // rank's workspace, `generation` changes whenever it is reallocated; `pinned`/`scratch` = small host / device staging
+    // areas (>= 1 KiB).  NCCL ranks exchange cudaIpc handles (re-opened only when a generation changed); in-process
+    // members exchange plain pointers.  Returns false - on every rank alike - when some mapping is not possible, in
+    // which case the callers keep to the collectives above.
+    bool map_peers(void* base, size_t bytes, uint64_t generation, void* pinned, void* scratch, cudaStream_t s);
+    // rank q's copy of the address `local` of this rank's workspace (workspaces are laid out identically)
+    template <class T>
+    T* peer(int q, T* local) const {
+        return reinterpret_cast<T*>(static_cast<char*>(peer_base_[q]) + (reinterpret_cast<char*>(local) - static_cast<char*>(own_base_)));
+    }
+    // all peer stores issued on the ranks' streams before this point are complete on every rank after it
+    void barrier(void* scratch, cudaStream_t s) const;
+
 private:
     void reset();
+    void close_peers();
+    void* own_base_ = nullptr;
+    void* peer_base_[8] = {nullptr};
+    uint64_t peer_gen_[8] = {0};
+    bool peer_opened_[8] = {false};  // peer_base_[q] came from cudaIpcOpenMemHandle
+    bool peers_ok_ = false;
     int rank_ = 0, world_ = 1;
     void* comm_ = nullptr;        // ncclComm_t
     LocalGroup* local_ = nullptr;  // not owned

@@ -15,9 +15,26 @@ constexpr int kThreads = 256;
 // One thread per row; the table is column-major so a warp reads 32 consecutive 16-byte cells per column.
 // WIDTH > 0: the row width is a compile-time constant (28 trace columns, 7 composition columns, 8 FRI values), so
 // the block loop is unrolled and the block lengths and flags are immediates; WIDTH = 0: any width.
-template <int WIDTH>
+// Where the digest of packed row t goes.  LocalLeaves: leaves[t] of this GPU.  PeerLeaves (multi-GPU, fused exchange):
+// row t of rank `me` is LDE row G t + me, i.e. leaf G (t mod chunk) + me of the subtree of rank t / chunk, and is
+// stored straight into that rank's node array over NVLink (peer pointers from Comm::map_peers) - the all-to-all of
+// digests and the unpacking pass never exist.
+struct LocalLeaves {
+    uint4* leaves;
+    __device__ __forceinline__ uint4* slot(uint64_t t) const { return leaves + 2 * t; }
+};
+struct PeerLeaves {
+    uint4* leaves[8];  // leaf area of every rank's subtree
+    uint32_t chunk_log, glog, me;
+    __device__ __forceinline__ uint4* slot(uint64_t t) const {
+        const uint64_t u = ((t & ((1ull << chunk_log) - 1)) << glog) + me;
+        return leaves[t >> chunk_log] + 2 * u;
+    }
+};
+
+template <int WIDTH, class Sink>
 __global__ void __launch_bounds__(kThreads) hash_rows_kernel(const uint4* __restrict__ table, uint64_t pitch,
-                                                            uint32_t width_rt, uint64_t rows, uint4* __restrict__ leaves) {
+                                                            uint32_t width_rt, uint64_t rows, Sink sink) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rows) return;
     const uint32_t width = WIDTH > 0 ? (uint32_t)WIDTH : width_rt;
@@ -38,8 +55,9 @@ __global__ void __launch_bounds__(kThreads) hash_rows_kernel(const uint4* __rest
         const uint32_t flags = (b == 0 ? B3_CHUNK_START : 0u) | (b == nblocks - 1 ? (B3_CHUNK_END | B3_ROOT) : 0u);
         b3_compress(cv, m, cells * 16, flags);
     }
-    leaves[2 * t] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
-    leaves[2 * t + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+    uint4* out = sink.slot(t);
+    out[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    out[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
 
 // dst[global_row_q(t) * UNITS + u] = src[(q * per_rank + t) * UNITS + u]: puts the all-gathered per-rank blocks
@@ -120,21 +138,36 @@ int merkle_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_
     return hash_rows_sharded(s, table, pitch, width, rows, RowShard(), nodes + 2 * rows);
 }
 
-int hash_rows_sharded(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard,
-                      uint4* digests) {
-    unsigned blocks = (unsigned)((local_rows + kThreads - 1) / kThreads);
+template <class Sink>
+static void launch_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t rows, const Sink& sink) {
+    unsigned blocks = (unsigned)((rows + kThreads - 1) / kThreads);
     {
-        LaunchScope ls(s, K_HASH_ROWS, local_rows * ((uint64_t)width * 16 + 32));
+        LaunchScope ls(s, K_HASH_ROWS, rows * ((uint64_t)width * 16 + 32));
         if (width == 28)
-            hash_rows_kernel<28><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, digests);
+            hash_rows_kernel<28><<<blocks, kThreads, 0, s>>>(table, pitch, width, rows, sink);
         else if (width == 7)
-            hash_rows_kernel<7><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, digests);
+            hash_rows_kernel<7><<<blocks, kThreads, 0, s>>>(table, pitch, width, rows, sink);
         else if (width == 8)
-            hash_rows_kernel<8><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, digests);
+            hash_rows_kernel<8><<<blocks, kThreads, 0, s>>>(table, pitch, width, rows, sink);
         else
-            hash_rows_kernel<0><<<blocks, kThreads, 0, s>>>(table, pitch, width, local_rows, digests);
+            hash_rows_kernel<0><<<blocks, kThreads, 0, s>>>(table, pitch, width, rows, sink);
     }
     EZK_CUDA(cudaGetLastError());
+}
+
+int hash_rows_sharded(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard,
+                      uint4* digests) {
+    launch_hash_rows(s, table, pitch, width, local_rows, LocalLeaves{digests});
+    return 1;
+}
+
+int hash_rows_to_peers(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard sh,
+                       uint4* const peer_leaves[8]) {
+    PeerLeaves sink;
+    for (int q = 0; q < 8; q++) sink.leaves[q] = peer_leaves[q];
+    sink.glog = sh.world_log, sink.me = sh.rank;
+    sink.chunk_log = ilog2_u64(local_rows) - sh.world_log;  // rows per destination = local_rows / world
+    launch_hash_rows(s, table, pitch, width, local_rows, sink);
     return 1;
 }
 

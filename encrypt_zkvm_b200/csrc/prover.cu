@@ -2,6 +2,7 @@
 // Stage order follows winter-prover 0.9.0 `Prover::prove`.
 #include "prover.h"
 #include <cstdlib>
+#include <unistd.h>
 #include <thread>
 #include "../../include/ezkvm_prover.h"
 #include "../../include/ezkvm_rescue_constants.h"
@@ -242,6 +243,7 @@ void GpuProver::reserve(size_t elems) {
     last_ = Last{};
     EZK_CUDA(cudaMalloc(&arena_.base, elems * sizeof(uint4)));
     arena_.capacity = elems;
+    arena_generation_ = ((uint64_t)getpid() << 32) | (uint64_t)(++arena_allocations_);
 }
 
 uint4* GpuProver::alloc(size_t elems) {
@@ -325,15 +327,35 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         if (packed) first_whole_layer = s, fri_elems += s;
         fri_elems += 2 * s + 8192;
     }
+    size_t fri_tree_elems = 0;  // subtrees of the sharded FRI layers
+    {
+        uint64_t s = L;
+        for (size_t k = 0; k < nlayers && sharded; k++, s /= 8) {
+            const uint64_t m = s / 8;
+            if (!(m >= shard_fri_min_rows && m >= (uint64_t)G * G)) break;
+            fri_tree_elems += 4 * (m >> glog) + 16;
+        }
+    }
     const size_t tcoef_cols = sharded ? (size_t)rounds * G : kWidth;
     const size_t allg_elems = sharded ? std::max<size_t>(first_whole_layer, (size_t)32768 * G) + 64 : 0;
     const size_t need = (host_columns ? (size_t)kWidth * n : 0) + tcoef_cols * n + (size_t)kWidth * L_local + (size_t)tmp_cols * L_local +
                         (sharded ? 0 : 8 * L) /* whole trees */ + 3 * L_local + L + (size_t)kCompCols * L_local + 2 * n +
                         (sharded ? 0 : 2 * L) + (size_t)(2 * kWidth + kCompCols) * eval_blocks + 4096 +
                         (sharded ? 4 * L_local + (size_t)cn * n + 8 * n + allg_elems + 8 * L_local /* subtrees */ : 0) + fri_elems +
-                        8192 + 32768 + 64 * 32 + (ops ? n / 16 + n / 4096 + 128 : 0);
+                        8192 + 32768 + 64 * 32 + (ops ? n / 16 + n / 4096 + 128 : 0) + fri_tree_elems + 256;
     reserve(need);
     reset_arena();
+    // Peer-visible part of the workspace first, so that it sits at the same offset on every rank whatever the input mode:
+    // the Merkle subtrees, whose leaves the other ranks' row-hash kernels write directly over NVLink (fused exchange)
+    uint4* d_peer_scratch = sharded ? alloc(128) : nullptr;  // handle exchange (first KiB), barrier words (second)
+    uint4* d_trees = sharded ? alloc(8 * L_local + fri_tree_elems) : nullptr;
+    size_t trees_used = 0;
+    bool peer_stores = false;
+    if (sharded && G > 1) {
+        const char* e = getenv("EZK_PEER_STORES");
+        const bool mapped = comm_.map_peers(arena_.base, arena_.capacity * sizeof(uint4), arena_generation_, pinned_, d_peer_scratch, stream_);
+        peer_stores = mapped && !(e && e[0] == '0');
+    }
     uint4* d_trace_in = host_columns ? alloc(kWidth * n) : nullptr;
     uint4* d_tcoef = alloc(tcoef_cols * n);
     uint4* d_tlde = alloc(kWidth * L_local);  // multi-GPU: this rank's rows only, packed order
@@ -384,7 +406,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         memcpy(pinned_, src, bytes);
         EZK_CUDA(cudaMemcpyAsync(dst, pinned_, bytes, cudaMemcpyHostToDevice, stream_));
     };
-    // commitment to a column-major table over the LDE domain (or to packed digests already in d_pack, table == nullptr)
+    // commitment to a column-major table of `leaves` rows (LDE tables, FRI layers; sharded: this rank's packed rows)
     auto commit = [&](const uint4* table, uint32_t width, uint64_t leaves, uint4* whole_nodes, ShardTree& tree) -> Hash32 {
         Hash32 root;
         tree.leaves = leaves;
@@ -397,32 +419,26 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         }
         const uint64_t ll = leaves >> glog;  // leaves of this rank's subtree
         // rank r's packed digests are those of rows r, r + G, ...: chunk q of them lies in rank q's leaf range
-        tree.split = true, tree.leaves_local = ll, tree.nodes = alloc(4 * ll);
+        tree.split = true, tree.leaves_local = ll, tree.nodes = d_trees + trees_used;
+        trees_used += (4 * ll + 15) & ~(size_t)15;
+        if (trees_used > 8 * L_local + fri_tree_elems) throw ProveFailure{EZK_ERR_INTERNAL, "subtree workspace exhausted"};
         const uint64_t chunk = ll >> glog;  // rows per destination
-        if (table && G > 1) {
-            // hash and exchange pipelined by destination, ring-shifted so that every step pairs each rank with one
-            // sender and one receiver: while the digests for rank me + k travel (auxiliary stream), the rows for rank
-            // me + k + 1 are being hashed; the own chunk comes last and needs no transfer
-            EZK_CUDA(cudaEventRecord(share_ev_[60], stream_));
-            EZK_CUDA(cudaStreamWaitEvent(aux_stream_, share_ev_[60], 0));  // d_recv / d_pack are free
-            for (uint32_t k = 1; k <= G; k++) {
-                const uint32_t dst = (me + k) % G, src = (me + G - k % G) % G;
-                uint4* out = k == G ? d_recv + 2 * (size_t)me * chunk : d_pack + 2 * (size_t)dst * chunk;
-                hash_rows_sharded(stream_, table + (size_t)dst * chunk, ll, width, chunk, sh, out);
-                if (k == G) break;
-                EZK_CUDA(cudaEventRecord(share_ev_[40 + k], stream_));
-                EZK_CUDA(cudaStreamWaitEvent(aux_stream_, share_ev_[40 + k], 0));
-                comm_.send_recv(out, (int)dst, d_recv + 2 * (size_t)src * chunk, (int)src, chunk * 32, aux_stream_);
-                count_launch();
-            }
-            EZK_CUDA(cudaEventRecord(share_ev_[61], aux_stream_));
-            EZK_CUDA(cudaStreamWaitEvent(stream_, share_ev_[61], 0));
-        } else {
-            if (table) hash_rows_sharded(stream_, table, ll, width, ll, sh, d_pack);
-            comm_.all_to_all(d_pack, d_recv, chunk * 32, stream_);
+        if (peer_stores) {
+            // exchange fused into the row hash: every digest goes straight to the leaf slot of the subtree that owns it
+            uint4* peer_leaves[8] = {nullptr};
+            for (uint32_t q = 0; q < G; q++) peer_leaves[q] = comm_.peer((int)q, tree.nodes) + 2 * ll;
+            hash_rows_to_peers(stream_, table, ll, width, ll, sh, peer_leaves);
+            comm_.barrier(d_peer_scratch + 64, stream_);  // all ranks' digests have landed
             count_launch();
-        }
+        } else {
+        // (measured and dropped: hashing and exchanging destination by destination in a ring-shifted pipeline of
+        // send/recv pairs - 7 small NCCL steps cost more than the one all-to-all they hide: trace commitment 2.2 -> 3.2 ms
+        // at 2^22 rows on 8 GPUs)
+        hash_rows_sharded(stream_, table, ll, width, ll, sh, d_pack);
+        comm_.all_to_all(d_pack, d_recv, chunk * 32, stream_);
+        count_launch();
         unpack_rows(stream_, d_recv, ll >> glog, glog, 2, tree.nodes + 2 * ll);
+        }
         merkle_build(stream_, tree.nodes, ll);
         uint4* d_roots = d_small + 1024;
         comm_.all_gather(tree.nodes + 2, d_roots, 32, stream_);  // the G subtree roots
@@ -880,8 +896,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
             Hash32 root;
             if (split) {
                 // a row is 8 positions at stride m, all of them = i mod G: in packed order again 8 values at stride m / G
-                hash_rows_sharded(stream_, cur, m >> glog, 8, m >> glog, RowShard(), d_pack);
-                root = commit(nullptr, 8, m, nullptr, layer.tree);
+                root = commit(cur, 8, m, nullptr, layer.tree);
             } else {
                 uint4* nodes = alloc(4 * m);
                 const bool was = sharded;

@@ -91,6 +91,8 @@ private:
     NttTables tables_;
     Comm comm_;
     Arena arena_;
+    uint64_t arena_generation_ = 0;   // changes with every (re)allocation: peers re-open their mapping of it
+    uint32_t arena_allocations_ = 0;
     uint8_t* pinned_ = nullptr;  // small host staging buffer
     size_t pinned_bytes_ = 0;
     // Staged trace upload for pageable caller memory (default; EZK_STAGED_UPLOAD=0 disables): a ring of page-locked slots
