@@ -18,11 +18,11 @@ int merkle_hash_rows(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_
 int hash_rows_sharded(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard sh,
                       uint4* digests);
 // multi-GPU, exchange fused into the hash: the digest of this rank's packed row t (LDE row world * t + rank) is stored
-// straight into the leaf area of the subtree it belongs to, on whichever rank holds it (peer_leaves[q] = rank q's
-// leaf area, reachable over NVLink).  local_rows must be a power of two >= world.  Callers put a group-wide barrier
-// between this launch and the first read of the leaves.
+// straight into the receive area of the rank whose subtree it belongs to (peer_recv[q] = rank q's receive area,
+// reachable over NVLink), at [rank][t mod chunk], chunk = local_rows / world - what an all-to-all would deliver.
+// local_rows must be a power of two >= world.  Callers put a group-wide barrier between this launch and unpack_rows.
 int hash_rows_to_peers(cudaStream_t s, const uint4* table, uint64_t pitch, uint32_t width, uint64_t local_rows, RowShard sh,
-                       uint4* const peer_leaves[8]);
+                       uint4* const peer_recv[8]);
 // dst[global_row_q(t)] = gathered[q][t] for the 2^world_log all-gathered blocks of per_rank items (units x 16 bytes each)
 int unpack_rows(cudaStream_t s, const uint4* gathered, uint64_t per_rank, uint32_t world_log, uint32_t units, uint4* dst);
 // builds all internal nodes from the leaves already stored in nodes[num_leaves..2*num_leaves)

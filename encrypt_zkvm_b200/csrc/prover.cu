@@ -349,6 +349,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     // the Merkle subtrees, whose leaves the other ranks' row-hash kernels write directly over NVLink (fused exchange)
     uint4* d_peer_scratch = sharded ? alloc(128) : nullptr;  // handle exchange (first KiB), barrier words (second)
     uint4* d_trees = sharded ? alloc(8 * L_local + fri_tree_elems) : nullptr;
+    uint4* d_recv = sharded ? alloc(2 * L_local) : nullptr;  // digests of this rank's leaf range, one chunk per sender
     size_t trees_used = 0;
     bool peer_stores = false;
     if (sharded && G > 1) {
@@ -375,7 +376,6 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     uint32_t* d_scan = ops ? reinterpret_cast<uint32_t*>(alloc(n / 4096 + 64)) : nullptr;
     // sharded: packed per-row products of this rank, the receive side of the exchanges
     uint4* d_pack = sharded ? alloc(2 * L_local) : nullptr;
-    uint4* d_recv = sharded ? alloc(2 * L_local) : nullptr;
     uint4* d_rloc = sharded ? alloc((size_t)cn * n) : nullptr;   // per-coset interpolations of the constraint evaluations
     uint4* d_rall = sharded ? alloc(8 * n) : nullptr;
     uint4* d_allg = sharded ? alloc(allg_elems) : nullptr;       // gathered FRI evaluations / opened rows of every rank
@@ -424,21 +424,22 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         if (trees_used > 8 * L_local + fri_tree_elems) throw ProveFailure{EZK_ERR_INTERNAL, "subtree workspace exhausted"};
         const uint64_t chunk = ll >> glog;  // rows per destination
         if (peer_stores) {
-            // exchange fused into the row hash: every digest goes straight to the leaf slot of the subtree that owns it
-            uint4* peer_leaves[8] = {nullptr};
-            for (uint32_t q = 0; q < G; q++) peer_leaves[q] = comm_.peer((int)q, tree.nodes) + 2 * ll;
-            hash_rows_to_peers(stream_, table, ll, width, ll, sh, peer_leaves);
+            // exchange fused into the row hash: every digest goes straight into the receive area of the rank that owns
+            // its subtree (NVLink peer stores), where an all-to-all would have put it
+            uint4* peer_recv[8] = {nullptr};
+            for (uint32_t q = 0; q < G; q++) peer_recv[q] = comm_.peer((int)q, d_recv);
+            hash_rows_to_peers(stream_, table, ll, width, ll, sh, peer_recv);
             comm_.barrier(d_peer_scratch + 64, stream_);  // all ranks' digests have landed
             count_launch();
         } else {
-        // (measured and dropped: hashing and exchanging destination by destination in a ring-shifted pipeline of
-        // send/recv pairs - 7 small NCCL steps cost more than the one all-to-all they hide: trace commitment 2.2 -> 3.2 ms
-        // at 2^22 rows on 8 GPUs)
-        hash_rows_sharded(stream_, table, ll, width, ll, sh, d_pack);
-        comm_.all_to_all(d_pack, d_recv, chunk * 32, stream_);
-        count_launch();
-        unpack_rows(stream_, d_recv, ll >> glog, glog, 2, tree.nodes + 2 * ll);
+            hash_rows_sharded(stream_, table, ll, width, ll, sh, d_pack);
+            comm_.all_to_all(d_pack, d_recv, chunk * 32, stream_);
+            count_launch();
         }
+        // (measured and dropped: hashing and exchanging destination by destination in a ring-shifted pipeline of NCCL
+        // send/recv pairs - 7 small steps cost more than the one all-to-all they hide: trace commitment 2.2 -> 3.2 ms
+        // at 2^22 rows on 8 GPUs)
+        unpack_rows(stream_, d_recv, ll >> glog, glog, 2, tree.nodes + 2 * ll);
         merkle_build(stream_, tree.nodes, ll);
         uint4* d_roots = d_small + 1024;
         comm_.all_gather(tree.nodes + 2, d_roots, 32, stream_);  // the G subtree roots
