@@ -27,6 +27,8 @@ using namespace dev;
 namespace {
 
 constexpr uint32_t kTileElems = 4096;  // field elements staged per CTA (64 KiB): S points x lanes
+constexpr int kDefaultOrderLog = 1;         // default of EZK_NTT_ORDER (-1 = column-major); measured: profiles/r02_ntt_cta_order_ab.log
+constexpr int kDefaultFinalOrderLog = -1;   // default of EZK_NTT_FINAL_ORDER (the final pass)
 
 // lanes = independent transforms handled side by side by one CTA: enough of them to fill the 4096-element tile
 // (so that all 256 threads have a group of 8 in every step) and to make global segments 64..512 bytes
@@ -315,6 +317,7 @@ struct StridedArgs {
     uint32_t cs_log, cs_base, cs_step;  //   nc = 1 << cs_log cosets per column, c = cs_base + cs_step * (y % nc)
     uint32_t log_L;
     uint32_t inv;
+    uint32_t order_log;             // CTA order, see ntt_strided_pass
     const uint4* roots;             // two-level 2^28-th root table (forward or inverse)
     const uint4* tw;                // compact per-size tables (same direction)
     const uint4* big;               // optional full inter-pass twiddle table (see build_pass_table), else nullptr
@@ -389,17 +392,29 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_strided_pass(StridedArgs a)
     extern __shared__ uint4 tile[];
     const uint32_t lanes = 1u << a.lanes_log;
     const uint32_t tiles_per_hi = (uint32_t)((1ull << a.log_stride) >> a.lanes_log);
+    // Which (tile, column) this CTA takes.  CTAs are dispatched in the order of x + gridDim.x * y.  Column-major order
+    // (tile = x, column = y: the ~450 resident CTAs work on two columns) re-reads from DRAM whatever the columns share:
+    // the inter-pass twiddle table (every column needs all of it) and, in an LDE, the coefficient column that the 8
+    // coset copies read.  Tile-major order (order_log = k): 2^k adjacent tiles of ALL columns back to back, so the
+    // resident CTAs share one slab of the table and of the coefficients and both come from DRAM once; k > 0 keeps
+    // neighbouring 64-byte segments of a row (adjacent tiles) in flight together.
+    // (k = log2(gridDim.x) is the column-major order again: one formula, no branch)
+    const uint32_t lin = blockIdx.x + gridDim.x * blockIdx.y;
+    const uint32_t per = gridDim.y << a.order_log;  // CTAs per group of 2^k tiles
+    const uint32_t grp = lin / per, r = lin - grp * per;
+    const uint32_t by = r >> a.order_log;
+    const uint32_t bx = (grp << a.order_log) | (r & ((1u << a.order_log) - 1));
     StridedPass P;
-    P.lo0 = (blockIdx.x % tiles_per_hi) * lanes;
-    const uint64_t hi = blockIdx.x / tiles_per_hi;
+    P.lo0 = (bx % tiles_per_hi) * lanes;
+    const uint64_t hi = bx / tiles_per_hi;
     P.base = P.lo0 + (hi << (a.log_stride + a.log_s));
-    uint32_t col = blockIdx.y;
+    uint32_t col = by;
     if (a.coset_first) {
-        // coset-major launch order: the CTAs of all columns of one coset run back to back, so that coset's slice of
-        // the inter-pass twiddle table (N entries) is read from DRAM once and then served by L2 for the other columns
+        // coset-major column order: the CTAs of all columns of one coset run back to back, so that (in column-major
+        // order) that coset's slice of the inter-pass twiddle table is read from DRAM once and then served by L2
         const uint32_t real_cols = gridDim.y >> a.cs_log;
-        const uint32_t ci = blockIdx.y / real_cols;
-        col = ((blockIdx.y - ci * real_cols) << a.cs_log) | ci;
+        const uint32_t ci = by / real_cols;
+        col = ((by - ci * real_cols) << a.cs_log) | ci;
         P.coset = a.cs_base + a.cs_step * (col & ((1u << a.cs_log) - 1));
         P.src = a.src + (uint64_t)(col >> a.cs_log) * a.src_pitch;
     } else {
@@ -429,6 +444,7 @@ struct FinalArgs {
     uint32_t log_L;
     uint32_t inv;
     uint32_t cs_log, cs_base, cs_step;  // LDE: 1 << cs_log cosets are computed, coset k = cs_base + cs_step * k
+    uint32_t order_log;             // CTA order as in StridedArgs (the columns of a plain transform share the scale table)
     const uint4* roots;
     const uint4* tw;
     const uint4* off_tab;
@@ -507,7 +523,12 @@ template <int THREADS, int MINB, int INV>
 __global__ void __launch_bounds__(THREADS, MINB) ntt_final_pass(const __grid_constant__ FinalArgs a) {
     extern __shared__ uint4 tile[];
     const uint32_t lanes = 1u << a.lanes_log;
-    const uint32_t col = blockIdx.y;
+    // tile-major CTA order, see ntt_strided_pass
+    const uint32_t lin = blockIdx.x + gridDim.x * blockIdx.y;
+    const uint32_t per = gridDim.y << a.order_log;
+    const uint32_t grp = lin / per, r = lin - grp * per;
+    const uint32_t col = r >> a.order_log;
+    const uint32_t bx = (grp << a.order_log) | (r & ((1u << a.order_log) - 1));
     FinalPass P;
     P.a = &a;
     P.log_H = a.log_n - a.log_s;  // log2(runs per column)
@@ -521,8 +542,8 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_final_pass(const __grid_con
             // run index hi' = rest + (H / n_p) * j_p ; the tile owns j_p = jp0 .. jp0+lanes-1 for one `rest`
             const uint32_t log_rest = P.log_H - a.log_top;
             const uint32_t tiles_per_rest = (1u << a.log_top) >> a.lanes_log;
-            const uint64_t rest = blockIdx.x / tiles_per_rest;
-            const uint32_t jp0 = (blockIdx.x % tiles_per_rest) * lanes;
+            const uint64_t rest = bx / tiles_per_rest;
+            const uint32_t jp0 = (bx % tiles_per_rest) * lanes;
             P.run0 = rest + ((uint64_t)jp0 << log_rest);
             P.run_step = 1ull << log_rest;
             P.out_base = (rest << a.log_top) + jp0;  // j_p + n_p * rest
@@ -533,8 +554,8 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_final_pass(const __grid_con
         // tile write adjacent rows of the packed output
         const uint32_t lj_log = a.lanes_log - a.lanes_c_log;
         const uint32_t halves_log = a.cs_log - a.lanes_c_log;
-        const uint64_t hp = blockIdx.x >> halves_log;  // run tile
-        P.coset0 = (blockIdx.x & ((1u << halves_log) - 1)) << a.lanes_c_log;
+        const uint64_t hp = bx >> halves_log;  // run tile
+        P.coset0 = (bx & ((1u << halves_log) - 1)) << a.lanes_c_log;
         P.src = a.mode == 1 ? a.src + (((uint64_t)col * a.src_pitch) << a.cs_log) : a.src + (uint64_t)col * a.src_pitch;
         if (a.passes <= 1) {
             P.run0 = hp, P.run_step = 0, P.out_base = 0;
@@ -760,6 +781,27 @@ const uint4* scale_table(const NttTables& t, cudaStream_t s, uint32_t log_n, con
     return st->d;
 }
 
+// CTA order of a strided pass (see ntt_strided_pass): tile-major in groups of 2^k adjacent tiles, k from
+// EZK_NTT_ORDER (read per launch: the A/B tool switches it inside one process; -1 = column-major grid order)
+uint32_t order_log_for(dim3 grid, int k) {
+    uint32_t log_gx = 0;
+    while ((1u << log_gx) < grid.x) log_gx++;
+    if ((1u << log_gx) != grid.x) throw CudaError("ntt: tiles per column must be a power of two");
+    if ((uint64_t)grid.x * grid.y >= (1ull << 32)) throw CudaError("ntt: grid too large");
+    return k < 0 || (uint32_t)k > log_gx ? log_gx : (uint32_t)k;  // log2(grid.x) = column-major
+}
+uint32_t strided_order_log(dim3 grid) {
+    int k = kDefaultOrderLog;
+    if (const char* e = getenv("EZK_NTT_ORDER")) k = atoi(e);
+    return order_log_for(grid, k);
+}
+
+uint32_t final_order_log(dim3 grid) {
+    int k = kDefaultFinalOrderLog;
+    if (const char* e = getenv("EZK_NTT_FINAL_ORDER")) k = atoi(e);
+    return order_log_for(grid, k);
+}
+
 // strided passes p..2 over `ncols` arrays of n elements: the first pass reads `first_src` and writes `buf`,
 // later passes run in place in `buf`.  With `coset` the first pass reads coefficient column y/8 and applies the
 // coset factor w_L^(c*m), c = y%8 (LDE).
@@ -785,6 +827,7 @@ int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log
         a.tw = StridedPass::kPreTw ? (inverse ? t.twp_inv : t.twp_fwd) : (inverse ? t.tw_inv : t.tw_fwd);
         a.big = pass_table(t, s, inverse, a.coset_first != 0, log_stride + a.log_s, log_stride, log_L);
         dim3 grid((unsigned)(((uint64_t)1 << (log_n - pl.log_d[i])) >> a.lanes_log), ncols);
+        a.order_log = strided_order_log(grid);
         {
             // compulsory traffic: every element of every column read once and written once (the 8 coset copies of
             // an LDE first pass share one read of the coefficient column)
@@ -929,6 +972,7 @@ int ntt_columns(const NttTables& t, cudaStream_t s, const uint4* src, uint64_t s
     a.scale_tab = scale ? scale_table(t, s, log_n, sc) : nullptr;
     uint64_t runs = 1ull << (log_n - pl.log_d[0]);
     dim3 grid((unsigned)(pl.passes >= 2 ? runs >> a.lanes_log : 1), ncols);
+    a.order_log = final_order_log(grid);
     {
         LaunchScope ls(s, K_NTT_FINAL, ((uint64_t)ncols << log_n) * 32);
         launch_final(grid, tile_bytes(a.log_s, a.lanes_log), s, a);
@@ -983,6 +1027,7 @@ int lde_columns(const NttTables& t, cudaStream_t s, const uint4* coeff, uint64_t
         a.src = tmp, a.src_pitch = n;
     }
     dim3 grid((unsigned)(((1ull << (log_n - pl.log_d[0])) >> lanes_j_log) << (cs.count_log - a.lanes_c_log)), ncols);
+    a.order_log = final_order_log(grid);
     {
         const uint64_t elems = (uint64_t)ncols << log_n, outs = elems << cs.count_log;
         LaunchScope ls(s, K_NTT_FINAL, (pl.passes == 1 ? elems + outs : 2 * outs) * 16);
