@@ -1,10 +1,12 @@
-"""A/B of the CTA order of the NTT passes (EZK_NTT_ORDER / EZK_NTT_FINAL_ORDER, read per launch) inside ONE process:
-for every setting one warm-up proof and `reps` measured proofs of a device-resident trace; prints the per-kernel times
-of the NTT passes, the stage times and the proof digest (every setting must give the same bytes).
+"""A/B of the run-time knobs of the NTT passes (environment variables the library reads per launch: EZK_NTT_ORDER,
+EZK_NTT_FINAL_ORDER, EZK_NTT_STAGE) inside ONE process: for every setting one warm-up proof and `reps` measured proofs
+of a device-resident trace; prints the per-kernel times of the NTT passes, the stage times and the proof digest (every
+setting must give the same bytes).
 
-    python tools/ntt_order_ab.py [log_n] [kind] [reps]
+    python tools/ntt_order_ab.py [log_n] [kind] [reps] [NAME=V,NAME=V ...]
 
--1 = column-major (plain grid order), k >= 0 = tile-major in groups of 2^k adjacent tiles (see ntt_strided_pass).
+EZK_NTT_ORDER: -1 = column-major (plain grid order), k >= 0 = tile-major in groups of 2^k adjacent tiles (see
+ntt_strided_pass).  EZK_NTT_STAGE: bit 0 strided / bit 1 final passes stage first-step inputs with cp.async.
 """
 import hashlib
 import json
@@ -35,13 +37,20 @@ dev = torch.from_numpy(trace.view(np.int64)).to("cuda:0")
 torch.cuda.synchronize()
 p = ezk.ExecutionProver(ezk.ProofOptions(), program_hash, outputs, ezk.ServerKey())
 
-settings = [(-1, -1), (0, -1), (1, -1), (2, -1), (3, -1), (5, -1), (-1, 0), (-1, 1), (-1, 3), (1, 1), (2, 2), (-1, -1)]
+settings = ["EZK_NTT_ORDER=-1", "EZK_NTT_ORDER=0", "EZK_NTT_ORDER=1", "EZK_NTT_ORDER=2", "EZK_NTT_ORDER=3", "EZK_NTT_ORDER=5",
+            "EZK_NTT_FINAL_ORDER=0", "EZK_NTT_FINAL_ORDER=1", "EZK_NTT_FINAL_ORDER=3", "EZK_NTT_ORDER=-1"]
 if len(sys.argv) > 4:
-    settings = [tuple(int(v) for v in s.split(",")) for s in sys.argv[4:]]
+    settings = sys.argv[4:]  # each "NAME=V,NAME=V" (an empty string or "-" = the defaults)
 digests = set()
-for so, fo in settings:
-    os.environ["EZK_NTT_ORDER"] = str(so)
-    os.environ["EZK_NTT_FINAL_ORDER"] = str(fo)
+touched = set()
+for setting in settings:
+    for name in touched:
+        os.environ.pop(name, None)
+    for kv in setting.split(","):
+        if "=" in kv:
+            name, v = kv.split("=")
+            os.environ[name] = v
+            touched.add(name)
     p.prove_device(dev.data_ptr(), 1 << log_n)  # warm-up (tables, caches)
     ezk.profile_enable(True)
     ezk.profile_reset()
@@ -55,7 +64,7 @@ for so, fo in settings:
     digests.add(d)
     k = {name: round(v["ms"] / reps, 3) for name, v in prof.items() if name.startswith("ntt_")}
     st = {name: round(v, 3) for name, v in p.stage_times_ms().items() if name in ("trace_lde", "composition", "deep")}
-    print(json.dumps({"log_n": log_n, "strided_order": so, "final_order": fo, "device_ms": round(ms, 3), "kernels": k,
+    print(json.dumps({"log_n": log_n, "env": setting, "device_ms": round(ms, 3), "kernels": k,
                       "stages_last": st, "sha256_16": d}), flush=True)
 print("identical bytes under every setting:", len(digests) == 1)
 p.close()
