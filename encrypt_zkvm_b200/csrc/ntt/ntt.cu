@@ -336,6 +336,7 @@ struct StridedPass {
     const uint4* big;  // big[(coset << log_N) + (j << log_stride) + lo] = w_L^(lo (8 j + coset)) (w_N^(lo j) for plain passes)
     uint64_t base;
     uint32_t lo0, log_stride, log_N, coset, log_L;
+    uint32_t hi_shift;  // log_stride - (log_L - EZK_TAB_BITS), see load
     // LDE first pass: the coset factor w_L^(c * idx), idx = lo + stride * m, splits into w_L^(c * stride * m)
     // (applied on load: exponent with >= 14 trailing zero bits in the 2^28 table -> one load, no product) and
     // w_L^(c * lo), constant along the transform, which is folded into the output twiddle's exponent:
@@ -362,7 +363,9 @@ struct StridedPass {
     __device__ __forceinline__ fe load(A& ar, const In& in, int p) const {
         fe v = fe_load(in.ptr + p * in.step);
         const uint32_t m = in.m0 + p * in.mstep;
-        if (coset != 0 && m != 0) v = ar.mul(v, root_pow(ar, roots, log_L, ((uint64_t)coset * m) << log_stride));
+        // w_L^(c m stride): stride >= L / 2^14 (run_strided checks it), so the exponent is a multiple of 2^14 in the
+        // two-level 2^28-th root table and the factor is one load from its upper level
+        if (coset != 0 && m != 0) v = ar.mul(v, fe_ldg(roots + EZK_TAB_SIZE + (((coset * m) << hi_shift) & (EZK_TAB_SIZE - 1))));
         return v;
     }
     __device__ __forceinline__ Out begin_out(uint32_t lane, uint32_t jg, uint32_t log_s) const {
@@ -370,16 +373,16 @@ struct StridedPass {
         const uint64_t at = ((uint64_t)jg << log_stride) + lo0 + lane;
         out.ptr = dst + base - lo0 + at;
         out.step = 1ull << (log_s - 3 + log_stride);
-        out.tab = big ? big + kPassTableWords * (((uint64_t)coset << log_N) + at) : nullptr;
+        out.tab = big + kPassTableWords * (((uint64_t)coset << log_N) + at);  // used when big != nullptr
         out.lo = lo0 + lane, out.j0 = jg, out.jstep = 1u << (log_s - 3);
         return out;
     }
     template <class A>
     __device__ __forceinline__ fe finish(A& ar, const Out& out, int p, fe v) const {
 #if EZK_NTT_PRE_PASS_TABLE
-        if (out.tab) return ar.mul_pre(v, fe_pre_ldg(out.tab + 4 * p * out.step));
+        if (big) return ar.mul_pre(v, fe_pre_ldg(out.tab + 4 * p * out.step));
 #else
-        if (out.tab) return ar.mul(v, fe_ldg(out.tab + p * out.step));
+        if (big) return ar.mul(v, fe_ldg(out.tab + p * out.step));
 #endif
         const uint64_t ex = (uint64_t)out.lo * (((uint64_t)(out.j0 + p * out.jstep) << (log_L - log_N)) + coset);
         return ex != 0 ? ar.mul(v, root_pow(ar, roots, log_L, ex)) : v;
@@ -426,6 +429,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_strided_pass(StridedArgs a)
     P.big = a.big;
     P.log_stride = a.log_stride, P.log_N = a.log_stride + a.log_s;
     P.log_L = a.coset_first ? a.log_L : P.log_N;  // plain passes: exponent lo * j of w_N
+    P.hi_shift = a.log_stride + EZK_TAB_BITS - a.log_L;  // used with coset_first only
     tile_transform<INV>(P, tile, a.log_s, a.lanes_log, a.tw);
 }
 
@@ -820,6 +824,7 @@ int run_strided(const NttTables& t, cudaStream_t s, const Plan& pl, uint32_t log
         a.lanes_log = lanes_log_for(a.log_s);
         if (a.lanes_log > log_stride) a.lanes_log = log_stride;
         a.coset_first = (first && cs) ? 1 : 0;
+        if (a.coset_first && log_stride + EZK_TAB_BITS < log_L) throw CudaError("ntt: coset factor is not in the upper table level");
         if (cs) a.cs_log = cs->count_log, a.cs_base = cs->base, a.cs_step = cs->step;
         a.log_L = log_L;
         a.inv = inverse ? 1 : 0;
