@@ -144,7 +144,7 @@ bool GpuProver::use_staged_upload(const uint8_t* const* host_columns) {
     }
     if (!copy_pool_) {
         const unsigned hw = std::thread::hardware_concurrency();
-        unsigned threads = std::max(1u, std::min(4u, hw / 2));
+        unsigned threads = std::max(1u, std::min(8u, hw / 2));  // pieces are claimed dynamically: late threads cost nothing
         if (const char* t = getenv("EZK_STAGE_THREADS")) {  // measurement knob (tools/pageable_e2e.py)
             const long k = atol(t);
             if (k >= 1 && k <= 32) threads = (unsigned)k;

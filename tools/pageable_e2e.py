@@ -1,6 +1,6 @@
 """End-to-end proofs from a PAGEABLE host trace (what a Rust `Vec<BaseElement>` column is), with the plain upload
 and with the staged upload (the default for unregistered memory; EZK_STAGED_UPLOAD=0 disables it;
-csrc/host/copy_pool.h), for 1 / 2 / default / 8 copy threads.  Torch-free; prints one JSON line and writes it to
+csrc/host/copy_pool.h), for 1 / 2 / 4 / 8 / the default number of copy threads.  Torch-free; prints one JSON line and writes it to
 profiles/r02_pageable_e2e_2p<log_n>.json.
 
     python tools/pageable_e2e.py [log_n] [kind] [steps] [device]
@@ -42,7 +42,7 @@ def measure(staged: bool):
 
 res["plain"], want = measure(False)
 same = True
-for threads in (0, 1, 2, 8):  # 0 = the library's default (min(4, cores / 2))
+for threads in (0, 1, 2, 4, 8):  # 0 = the library's default (min(8, cores / 2))
     if threads:
         os.environ["EZK_STAGE_THREADS"] = str(threads)
     res[f"staged_{threads}_threads" if threads else "staged"], got = measure(True)
