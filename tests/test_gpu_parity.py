@@ -52,6 +52,22 @@ def test_lde_matches_oracle(prover, oracle, log_n, width):
         assert np.array_equal(got[c], want), f"column {c}"
 
 
+@pytest.mark.parametrize("order", ["-1", "0", "2", "7"])
+def test_lde_is_independent_of_the_cta_order(prover, oracle, monkeypatch, order):
+    """The strided NTT passes take their (tile, column) from the linear CTA index (csrc/ntt/ntt.cu, EZK_NTT_ORDER, read
+    per launch): column-major (-1), tile-major in groups of 2^k tiles (k beyond log2(tiles) falls back to column-major).
+    Every order computes the same table; the default order is what every other test runs."""
+    monkeypatch.setenv("EZK_NTT_ORDER", order)
+    monkeypatch.setenv("EZK_NTT_FINAL_ORDER", order)
+    for log_n, width in [(11, 3), (13, 5), (16, 2)]:  # two-pass plans (one-pass transforms have no strided pass)
+        rng = np.random.default_rng(900 + log_n)
+        cols = rand_elems(rng, (width, 1 << log_n))
+        got = prover.stage_lde(cols)
+        for c in range(width):
+            _, want = oracle.lde_column(cols[c])
+            assert np.array_equal(got[c], want), f"order {order}, 2^{log_n}, column {c}"
+
+
 @pytest.mark.parametrize("rows,width", [(2, 1), (16, 28), (512, 7), (4096, 8), (1 << 14, 28), (1 << 15, 3)])
 def test_merkle_matches_oracle(prover, oracle, rows, width):
     rng = np.random.default_rng(300 + rows)
