@@ -124,6 +124,8 @@ GpuProver::GpuProver(int device) : device_(device) {
     }
     for (auto& e : aux_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : copy_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : col_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : grp_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : share_ev_) EZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
@@ -216,6 +218,8 @@ GpuProver::~GpuProver() {
     for (auto& e : ev_) cudaEventDestroy(e);
     for (auto& e : timer_ev_) cudaEventDestroy(e);
     for (auto& e : copy_ev_) cudaEventDestroy(e);
+    for (auto& e : col_ev_) cudaEventDestroy(e);
+    for (auto& e : grp_ev_) cudaEventDestroy(e);
     for (auto& e : share_ev_) cudaEventDestroy(e);
     cudaStreamDestroy(copy_stream_);
     for (auto& e : aux_ev_) cudaEventDestroy(e);
@@ -311,7 +315,10 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
     // ---- workspace (16-byte elements; the arena is sized once per trace length and kept) ----
     // transform scratch in columns of L_local elements: sharded batches hold <= 8 columns, the host path 2-column groups,
     // the DEEP step 2 columns; the composition columns are extended in groups that fit
-    const uint32_t tmp_cols = sharded ? 8 : std::max(2u, host_columns ? 2u : lde_group);
+    // columns per launch of a host trace: groups grow from 1 to this cap while the upload runs ahead (see below)
+    uint32_t host_group_cap = std::min(8u, lde_group);
+    if (const char* e = getenv("EZK_HOST_GROUP_CAP")) host_group_cap = (uint32_t)std::min<long>(lde_group, std::max<long>(1, atol(e)));
+    const uint32_t tmp_cols = sharded ? 8 : std::max(2u, host_columns ? host_group_cap : lde_group);
     const uint32_t comp_group = std::min(kCompCols, tmp_cols);
     size_t fri_elems = 0;
     uint64_t first_whole_layer = 0;  // sharded: size of the first FRI layer that is gathered onto every rank
@@ -574,32 +581,70 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
             extend_batch(((rounds - 1) / rb) * rb);
             }
         } else if (host_columns) {
-            // Upload and transform in column groups: the copy of group k+1 (copy stream) overlaps the
-            // interpolation + LDE of group k (compute stream).  Columns are independent until the row hash.
-            constexpr uint32_t kGroup = 2;  // small groups: the pipeline fills after 2 columns (32 MiB at 2^20), not 7
-            EZK_CUDA(cudaEventRecord(copy_ev_[kWidth / kGroup], stream_));
-            EZK_CUDA(cudaStreamWaitEvent(copy_stream_, copy_ev_[kWidth / kGroup], 0));  // the arena may still be in use
+            // Upload and transform overlap: columns travel on the copy stream while the interpolation + LDE of earlier
+            // columns run on the compute stream (columns are independent until the row hash).  How many columns go into
+            // one launch is decided as they arrive: a launch goes out at once when the compute stream is empty (the first
+            // column, or an upload-bound host), and otherwise only when it is at least as large as the launch that is
+            // running and nothing else is queued behind that one - so while the upload runs ahead of the transforms the
+            // groups grow (1, 1, 2, 2, 3, ... up to host_group_cap columns: large launches are 10-15 % more efficient
+            // than 2-column ones) and the GPU never waits for a group to fill.
+            EZK_CUDA(cudaEventRecord(copy_ev_[15], stream_));
+            EZK_CUDA(cudaStreamWaitEvent(copy_stream_, copy_ev_[15], 0));  // the arena may still be in use
             const bool staged = use_staged_upload(host_columns);
             uint64_t chunk = 0;
-            for (uint32_t g = 0; !staged && g < kWidth / kGroup; g++) {
-                for (uint32_t c = g * kGroup; c < (g + 1) * kGroup; c++)
-                    if (uploaded(c))
+            if (!staged)
+                for (uint32_t c = 0; c < kWidth; c++)
+                    if (uploaded(c)) {
                         EZK_CUDA(cudaMemcpyAsync(d_trace_in + (size_t)c * n, host_columns[c], n * 16, cudaMemcpyHostToDevice,
                                                  copy_stream_));
-                EZK_CUDA(cudaEventRecord(copy_ev_[g], copy_stream_));
-            }
-            for (uint32_t g = 0; g < kWidth / kGroup; g++) {
-                if (staged) {  // this thread feeds the ring, so the transforms of a group are queued as soon as it is sent
-                    for (uint32_t c = g * kGroup; c < (g + 1) * kGroup; c++)
-                        if (uploaded(c)) staged_copy_column(d_trace_in + (size_t)c * n, host_columns[c], n * 16, chunk);
-                    EZK_CUDA(cudaEventRecord(copy_ev_[g], copy_stream_));
+                        EZK_CUDA(cudaEventRecord(col_ev_[c], copy_stream_));
+                    }
+            uint32_t launched = 0, ngroups = 0, head = 0;  // groups [head, ngroups) may still be running
+            uint32_t group_cols[32];
+            auto launch = [&](uint32_t c1) {  // transforms of columns [launched, c1), behind the upload of the last of them
+                for (uint32_t c = c1; c-- > launched;)
+                    if (uploaded(c)) {
+                        EZK_CUDA(cudaStreamWaitEvent(stream_, col_ev_[c], 0));  // the copy stream is in order
+                        break;
+                    }
+                if (launched == 0) mark();
+                const uint32_t cols = c1 - launched;
+                const size_t c0 = launched;
+                check_canonical(stream_, d_trace_in + c0 * n, (size_t)cols * n, d_flag_);
+                ntt_columns(tables_, stream_, d_trace_in + c0 * n, n, d_tcoef + c0 * n, n, d_tmp, cols, log_n, true, &sc);
+                lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L, L, d_tmp, cols, log_n, cs);
+                EZK_CUDA(cudaEventRecord(grp_ev_[ngroups], stream_));
+                group_cols[ngroups++] = cols;
+                launched = c1;
+            };
+            auto should_launch = [&](uint32_t avail, bool all_sent) {
+                if (avail == 0) return false;
+                while (head < ngroups && cudaEventQuery(grp_ev_[head]) == cudaSuccess) head++;
+                cudaGetLastError();  // cudaErrorNotReady is not an error
+                const uint32_t pending = ngroups - head;
+                if (pending == 0 || avail >= host_group_cap) return true;
+                if (pending == 1) return avail >= group_cols[head] || all_sent;
+                return false;
+            };
+            if (staged) {  // this thread feeds the ring: decide after every column it has sent
+                for (uint32_t c = 0; c < kWidth; c++) {
+                    if (uploaded(c)) {
+                        staged_copy_column(d_trace_in + (size_t)c * n, host_columns[c], n * 16, chunk);
+                        EZK_CUDA(cudaEventRecord(col_ev_[c], copy_stream_));
+                    }
+                    if (should_launch(c + 1 - launched, false)) launch(std::min(c + 1, launched + host_group_cap));
                 }
-                EZK_CUDA(cudaStreamWaitEvent(stream_, copy_ev_[g], 0));
-                if (g == 0) mark();
-                const size_t c0 = (size_t)g * kGroup;
-                check_canonical(stream_, d_trace_in + c0 * n, kGroup * n, d_flag_);
-                ntt_columns(tables_, stream_, d_trace_in + c0 * n, n, d_tcoef + c0 * n, n, d_tmp, kGroup, log_n, true, &sc);
-                lde_columns(tables_, stream_, d_tcoef + c0 * n, n, d_tlde + c0 * L, L, d_tmp, kGroup, log_n, cs);
+                while (launched < kWidth) launch(std::min(kWidth, launched + host_group_cap));
+            } else {  // all copies are queued: follow their completion
+                uint32_t ready = 0;
+                while (launched < kWidth) {
+                    while (ready < kWidth && (!uploaded(ready) || cudaEventQuery(col_ev_[ready]) == cudaSuccess)) ready++;
+                    cudaGetLastError();
+                    if (should_launch(ready - launched, ready == kWidth))
+                        launch(std::min(ready, launched + host_group_cap));
+                    else if (ready == launched)
+                        EZK_CUDA(cudaEventSynchronize(col_ev_[ready]));  // nothing to do until the next column is here
+                }
             }
         } else {
             mark();

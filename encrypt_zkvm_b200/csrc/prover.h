@@ -85,6 +85,8 @@ private:
     cudaStream_t stream_ = nullptr;
     cudaStream_t copy_stream_ = nullptr;  // host -> device trace upload, overlapped with the first transforms
     cudaEvent_t copy_ev_[16];
+    cudaEvent_t col_ev_[32];              // host trace: upload of column c done / transforms of launch group g queued behind it
+    cudaEvent_t grp_ev_[32];
     cudaStream_t aux_stream_ = nullptr;   // small independent kernels overlapped with latency-bound phases
     cudaEvent_t aux_ev_[4];
     cudaEvent_t share_ev_[64];            // multi-GPU: interpolation of a column round done / its all-gather done
