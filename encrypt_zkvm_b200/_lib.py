@@ -66,6 +66,7 @@ SIGNATURES = {
     "ezk_selftest_copy_pool": (C.c_int, [C.c_uint32, C.c_size_t]),
     "ezk_selftest_shard_layout": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64]),
     "ezk_selftest_host_field": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "ezk_selftest_launch_groups": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "ezk_prover_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "ezk_prover_destroy": (None, [_P]),
     "ezk_prover_prove": (C.c_int, [_P, C.POINTER(EzkTrace), C.POINTER(EzkPublicInputs), C.POINTER(EzkOptions),

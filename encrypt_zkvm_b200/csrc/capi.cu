@@ -3,6 +3,7 @@
 #include "../../include/ezkvm_prover.h"
 #include "common.h"
 #include "host/vm.h"
+#include "host/launch_groups.h"
 #include "dist/shard_layout.h"
 #include "prover.h"
 #include "trace/expand.cuh"
@@ -115,6 +116,54 @@ int ezk_selftest_copy_pool(uint32_t threads, size_t bytes) {
                 if (memcmp(dst.data() + shift, src.data() + shift, len) != 0 || dst[shift + len] != 0xEE || (shift && dst[shift - 1] != 0xEE))
                     throw ProveFailure{EZK_ERR_INTERNAL, "threaded copy differs from memcpy"};
             }
+    });
+}
+// Discrete-event replay of host/launch_groups.h: column c arrives at (c + 1) * upload_us, a launch of k columns takes
+// k * compute_us and starts when its last column is there and the launch before it has ended; the decision is taken
+// whenever a column arrives (the staged upload) and, once all have arrived, whenever a launch ends.
+int ezk_selftest_launch_groups(uint32_t columns, uint32_t cap, uint32_t upload_us, uint32_t compute_us, uint32_t* sizes_out,
+                               uint32_t* groups_out, uint64_t* idle_us_out) {
+    return guarded([&] {
+        if (columns == 0 || columns > 64 || cap == 0 || upload_us == 0 || compute_us == 0 || !sizes_out || !groups_out || !idle_us_out)
+            throw ProveFailure{EZK_ERR_INVALID_ARGUMENT, "bad self-test arguments"};
+        std::vector<uint64_t> ends;   // end time of every launch, in order
+        std::vector<uint32_t> sizes;
+        uint32_t launched = 0;
+        uint64_t idle = 0, gpu_free = 0;
+        auto decide = [&](uint64_t now, uint32_t arrived) {
+            uint32_t head = 0;
+            while (head < ends.size() && ends[head] <= now) head++;
+            const uint32_t pending = (uint32_t)ends.size() - head;
+            const uint32_t avail = arrived - launched;
+            if (!host_group_ready(avail, pending, pending ? sizes[head] : 0, cap, arrived == columns)) return false;
+            const uint32_t k = std::min(avail, cap);
+            const uint64_t ready_at = (uint64_t)(launched + k) * upload_us;  // its last column is on the device
+            const uint64_t start = std::max({now, ready_at, gpu_free});
+            if (launched > 0 && start > gpu_free) idle += start - gpu_free;
+            gpu_free = start + (uint64_t)k * compute_us;
+            ends.push_back(gpu_free), sizes.push_back(k);
+            launched += k;
+            return true;
+        };
+        for (uint32_t c = 0; c < columns; c++) decide((uint64_t)(c + 1) * upload_us, c + 1);
+        uint64_t now = (uint64_t)columns * upload_us;
+        for (int guard = 0; launched < columns; guard++) {
+            if (guard > 1000) throw ProveFailure{EZK_ERR_INTERNAL, "the launch rule stalls"};
+            if (decide(now, columns)) continue;
+            uint64_t next = UINT64_MAX;  // nothing to launch yet: the next decision comes when a launch ends
+            for (uint64_t e : ends)
+                if (e > now) next = std::min(next, e);
+            if (next == UINT64_MAX) throw ProveFailure{EZK_ERR_INTERNAL, "the launch rule waits for nothing"};
+            now = next;
+        }
+        uint32_t total = 0;
+        for (size_t i = 0; i < sizes.size(); i++) {
+            if (sizes[i] == 0 || sizes[i] > cap) throw ProveFailure{EZK_ERR_INTERNAL, "launch size out of range"};
+            sizes_out[i] = sizes[i], total += sizes[i];
+        }
+        if (total != columns) throw ProveFailure{EZK_ERR_INTERNAL, "columns lost or launched twice"};
+        *groups_out = (uint32_t)sizes.size();
+        *idle_us_out = idle;
     });
 }
 int ezk_selftest_host_field(const void* a, const void* b, size_t n, void* out4n) {

@@ -10,6 +10,7 @@
 #include "compose/compose.cuh"
 #include "dist/shard_layout.h"
 #include "fri/fri.cuh"
+#include "host/launch_groups.h"
 #include "host/air_host.h"
 #include "merkle/merkle.cuh"
 #include "trace/expand.cuh"
@@ -583,11 +584,8 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
         } else if (host_columns) {
             // Upload and transform overlap: columns travel on the copy stream while the interpolation + LDE of earlier
             // columns run on the compute stream (columns are independent until the row hash).  How many columns go into
-            // one launch is decided as they arrive: a launch goes out at once when the compute stream is empty (the first
-            // column, or an upload-bound host), and otherwise only when it is at least as large as the launch that is
-            // running and nothing else is queued behind that one - so while the upload runs ahead of the transforms the
-            // groups grow (1, 1, 2, 2, 3, ... up to host_group_cap columns: large launches are 10-15 % more efficient
-            // than 2-column ones) and the GPU never waits for a group to fill.
+            // one launch is decided as they arrive (host/launch_groups.h): the groups grow 1, 1, 2, 2, 3, ... up to
+            // host_group_cap columns while the upload runs ahead, and the GPU never waits for a group to fill.
             EZK_CUDA(cudaEventRecord(copy_ev_[15], stream_));
             EZK_CUDA(cudaStreamWaitEvent(copy_stream_, copy_ev_[15], 0));  // the arena may still be in use
             const bool staged = use_staged_upload(host_columns);
@@ -622,9 +620,7 @@ std::vector<uint8_t> GpuProver::prove_impl(const uint8_t* const* host_columns, c
                 while (head < ngroups && cudaEventQuery(grp_ev_[head]) == cudaSuccess) head++;
                 cudaGetLastError();  // cudaErrorNotReady is not an error
                 const uint32_t pending = ngroups - head;
-                if (pending == 0 || avail >= host_group_cap) return true;
-                if (pending == 1) return avail >= group_cols[head] || all_sent;
-                return false;
+                return host_group_ready(avail, pending, pending ? group_cols[head] : 0, host_group_cap, all_sent);
             };
             if (staged) {  // this thread feeds the ring: decide after every column it has sent
                 for (uint32_t c = 0; c < kWidth; c++) {

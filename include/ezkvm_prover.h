@@ -97,6 +97,13 @@ int ezk_selftest_copy_pool(uint32_t threads, size_t bytes);
  * Needs no GPU.  Returns EZK_OK or EZK_ERR_INTERNAL. */
 int ezk_selftest_shard_layout(uint32_t world, uint32_t log_leaves, uint64_t seed);
 
+/* Host-side replay of the rule that sizes the interpolation + LDE launches of a host trace (csrc/host/launch_groups.h):
+ * `columns` columns arriving every upload_us, a launch of k columns taking k * compute_us, at most `cap` columns per
+ * launch.  Writes the launch sizes (up to `columns` entries), their number and the time the compute stream sat idle
+ * after its first launch.  Needs no GPU.  Returns EZK_OK, EZK_ERR_INVALID_ARGUMENT or EZK_ERR_INTERNAL (a column lost). */
+int ezk_selftest_launch_groups(uint32_t columns, uint32_t cap, uint32_t upload_us, uint32_t compute_us, uint32_t* sizes_out,
+                               uint32_t* groups_out, uint64_t* idle_us_out);
+
 /* Host-side self-test of the f128 arithmetic behind the transcript and the VM: for n pairs (a_i, b_i) of canonical
  * elements writes a_i * b_i (portable product), a_i * b_i (the product the Rescue sponge uses), a_i^2 and
  * a_i^INV_ALPHA (the sponge's addition chain) - 4 * n elements - for the caller to compare with big integers.

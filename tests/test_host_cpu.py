@@ -67,6 +67,32 @@ def test_threaded_copy_of_the_staged_upload(threads):
         assert _lib.lib.ezk_selftest_copy_pool(threads, size) == 0, _lib.lib.ezk_last_error().decode()
 
 
+def _launch_groups(columns, cap, upload_us, compute_us):
+    import ctypes as C
+    sizes, n, idle = (C.c_uint32 * 64)(), C.c_uint32(), C.c_uint64()
+    rc = _lib.lib.ezk_selftest_launch_groups(columns, cap, upload_us, compute_us, sizes, C.byref(n), C.byref(idle))
+    assert rc == 0, _lib.lib.ezk_last_error().decode()
+    return list(sizes[: n.value]), idle.value
+
+
+def test_launch_groups_of_a_host_trace():
+    """csrc/host/launch_groups.h (how many columns of a host trace go into one interpolation + LDE launch), replayed by
+    the library against a discrete-event model: every column is launched exactly once, no launch exceeds the cap, the
+    groups grow while the upload runs ahead of the transforms and stay at one column when the upload is the bottleneck."""
+    for cap in (1, 2, 4, 8, 14, 28):
+        for up, comp in [(400, 500), (335, 450), (600, 450), (100, 500), (500, 100), (1, 1000), (1000, 1)]:
+            sizes, _ = _launch_groups(28, cap, up, comp)
+            assert sum(sizes) == 28 and max(sizes) <= cap and min(sizes) >= 1
+    sizes, idle = _launch_groups(28, 8, 400, 500)          # compute-bound: growing groups, the GPU never waits
+    assert sizes[0] == 1 and idle == 0 and max(sizes) >= 3 and len(sizes) <= 16
+    assert all(b >= a for a, b in zip(sizes, sizes[1:-1]))  # non-decreasing (the last launch takes what is left)
+    sizes, _ = _launch_groups(28, 8, 100, 500)              # upload far ahead: the cap is reached
+    assert max(sizes) == 8 and len(sizes) <= 8
+    sizes, _ = _launch_groups(28, 8, 600, 450)              # upload-bound: one column per launch, shortest tail
+    assert sizes == [1] * 28
+    assert _lib.lib.ezk_selftest_launch_groups(0, 8, 1, 1, None, None, None) != 0
+
+
 def test_no_cpu_fallback_without_a_device():
     """On a box without a GPU every compute entry point must fail with EZK_ERR_NO_DEVICE, never compute on the CPU."""
     if ezk.device_count() > 0:
