@@ -24,7 +24,7 @@ with tempfile.TemporaryDirectory() as tmp:
 
 funcs = re.split(r"\n\s*Function : ", sass)[1:]
 doc = ["# SASS of the field primitives (sm_100a)", "",
-       "`python tools/sass_primitives.py` — `" + " ".join(cmd[:8]) + " …`, " + "; ".join(ver) + ".",
+       "`python tools/sass_primitives.py` — `nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -cubin tools/sass/field_primitives.cu`, " + "; ".join(ver) + ".",
        "Counts are the instructions strictly between the last operand load (`LDG`) and the first result store (`STG`)",
        "of each probe kernel: the primitive itself, the flag update (`VIMNMX`) of the branch-free forms and the address",
        "of the store (one `LDC` + one `IMAD.WIDE`, which ptxas schedules into this window) - subtract 2 for the primitive",
