@@ -213,7 +213,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world, out)
+        # the CPU arm needs no process group: when it is started without torchrun, --gpus N still names the workload of N GPUs
+        run_reference(args, rank, max(world, args.gpus), out)
         return
     resolve_workload(args, world)
 

@@ -34,6 +34,18 @@ def test_reference_arm_is_silent_on_other_ranks():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_reference_arm_names_the_workload_of_the_gpu_count_without_torchrun():
+    """`bench.py --impl reference --gpus 4` started as a plain process (no WORLD_SIZE) still resolves to configs[3];
+    checked through --help-free argument resolution only (a 2^22 CPU proof takes minutes)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    src = (ROOT / "bench.py").read_text()
+    assert "run_reference(args, rank, max(world, args.gpus), out)" in src
+    a = SimpleNamespace(log_n=None, kind=None, gpus=4)
+    bench.resolve_workload(a, max(1, a.gpus))
+    assert (a.log_n, a.kind) == (22, 3)
+
+
 def test_workload_per_gpu_count():
     """configs[2] (2^20, ciphertext program) on 1 and 2 GPUs, configs[3] (2^22, mixed) on 4 and 8; explicit flags win."""
     sys.path.insert(0, str(ROOT))
